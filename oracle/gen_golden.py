@@ -1,0 +1,284 @@
+"""Generate the committed golden fixtures in tests/golden/ by running the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE.  Run in the build container only (needs /root/reference):
+
+    python oracle/gen_golden.py            # writes tests/golden/*.pt
+
+Every tensor stored here is an output of reference code (cited per block) on seeded inputs that
+are stored next to it, so the fixtures are self-contained and do not depend on RNG reproducibility
+across machines.  The reference publishes no golden vectors of its own.
+"""
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle.ref_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def tiny_llama(dtype=torch.float32):
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    cfg = LlamaConfig(
+        hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+        num_key_value_heads=4, vocab_size=512, max_position_embeddings=128, tie_word_embeddings=False,
+    )
+    torch.manual_seed(0)
+    m = LlamaForCausalLM(cfg).to(dtype).eval()
+    m.config.use_cache = False
+    return m
+
+
+def calib_ids(n=4, t=32, vocab=512):
+    g = torch.Generator().manual_seed(1234)
+    return [torch.randint(0, vocab, (1, t), generator=g) for _ in range(n)]
+
+
+def woq_state(model):
+    return {k: v.clone() for k, v in model.state_dict().items()
+            if any(s in k for s in ("qweight", "qzeros", "scales", "g_idx", "input_scale")) and "bf16_to_fp8" not in k}
+
+
+def gen_rtn_pack():
+    """utility.py:272 quant_tensor, modules.py:321 pack / :413 recover / :594 forward."""
+    from neural_compressor.torch.algorithms.weight_only.modules import INCWeightOnlyLinear
+    from neural_compressor.torch.algorithms.weight_only.utility import quant_tensor, search_clip
+
+    cases = []
+    g = torch.Generator().manual_seed(7)
+    specs = [
+        # N, K, bits, group, scheme, quantile, full_range, dtype
+        (32, 64, 4, 32, "sym", 1.0, False, torch.float32),
+        (32, 64, 4, 32, "asym", 1.0, False, torch.float32),
+        (64, 256, 4, 128, "sym", 1.0, False, torch.float32),
+        (64, 256, 4, 128, "asym", 0.93, False, torch.float32),
+        (48, 300, 4, 128, "asym", 1.0, False, torch.float32),   # ragged tail group (utility.py:334-376)
+        (48, 300, 4, 128, "sym", 1.0, False, torch.float32),
+        (40, 96, 4, -1, "sym", 1.0, True, torch.float32),        # per-channel, full_range (sign flip)
+        (40, 96, 8, 32, "sym", 1.0, False, torch.float32),
+        (40, 96, 8, 32, "asym", 1.0, False, torch.float32),
+        (40, 96, 2, 32, "asym", 1.0, False, torch.float32),
+        (24, 128, 3, 32, "sym", 1.0, False, torch.float32),      # n_pack = 10 (32 // 3)
+        (32, 128, 4, 32, "sym", 1.0, False, torch.float16),
+        (32, 128, 4, 32, "asym", 1.0, False, torch.float16),
+        (32, 128, 4, 32, "sym", 0.97, False, torch.bfloat16),
+    ]
+    for (n, k, bits, gs, scheme, quantile, fr, dt) in specs:
+        w = (torch.randn(n, k, generator=g) * 0.05).to(dt)
+        if scheme == "asym":
+            w[0].abs_()          # an all-positive row: wmin clamps to 0
+        w[1].zero_()             # an all-zero row: the (0,0) -> (-1,+1) / amax=1 branch
+        wq = w.clone()
+        codes, scale, zp = quant_tensor(wq, bits=bits, group_size=gs, scheme=scheme, quantile=quantile,
+                                        return_int=True, full_range=fr)
+        case = dict(N=n, K=k, bits=bits, group_size=gs, scheme=scheme, quantile=quantile, full_range=fr,
+                    W=w, codes=codes.clone(), scale=scale.clone(), zp=None if zp is None else zp.clone())
+        fq = quant_tensor(w.clone(), bits=bits, group_size=gs, scheme=scheme, quantile=quantile,
+                          return_int=False, full_range=fr)
+        case["fake_quant"] = fq.clone()
+        eff_g = k if (gs == -1 or k < gs) else gs
+        bias = (torch.randn(n, generator=g) * 0.1)
+        mod = INCWeightOnlyLinear(k, n, dtype="int", bits=bits, group_size=eff_g, zp=zp is not None,
+                                  bias=True, device="cpu")
+        mod.pack(codes.clone(), scale.clone(), None if zp is None else zp.clone(), bias)
+        case.update(qweight=mod.qweight.clone(), qzeros=mod.qzeros.clone(), scales16=mod.scales.clone(),
+                    bias=bias, eff_group=eff_g)
+        up = mod.unpack()
+        case.update(unpacked_codes=up.get("int_weight").clone(), unpacked_zp=up.get("zp").clone())
+        case["recovered"] = mod.recover().clone()
+        x = torch.randn(3, k, generator=g)
+        case["x"] = x
+        case["y"] = mod(x).clone()
+        cases.append(case)
+    # RTN mse clip search (utility.py:439-480)
+    lin = torch.nn.Linear(128, 32)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(32, 128, generator=g) * 0.05)
+        lin.weight[:, 5] *= 8
+    clip = dict(W=lin.weight.detach().clone(),
+                ratio_sym=search_clip(lin, 4, 32, "sym", "int", False),
+                ratio_asym=search_clip(lin, 4, 32, "asym", "int", False))
+    torch.save(dict(cases=cases, search_clip=clip), os.path.join(OUT, "rtn_pack.pt"))
+    print("rtn_pack:", len(cases), "cases")
+
+
+def gen_config1():
+    """BASELINE.json configs[0]: RTN INT4 g128 on nn.Linear(1024,1024) via the public API."""
+    from neural_compressor.torch.quantization import RTNConfig, convert, prepare
+
+    torch.manual_seed(0)
+    m = torch.nn.Linear(1024, 1024)
+    w = m.weight.detach().clone()
+    b = m.bias.detach().clone()
+    q = convert(prepare(m, RTNConfig(bits=4, group_size=128, use_sym=True, use_layer_wise=False)))
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(4, 1024, generator=g)
+    torch.save(dict(W_sum=w.double().sum().item(), W_abs_sum=w.double().abs().sum().item(), bias=b,
+                    qweight=q.qweight.clone(), qzeros=q.qzeros.clone(), scales=q.scales.clone(),
+                    x=x, y=q(x).clone()),
+               os.path.join(OUT, "config1_rtn_linear1024.pt"))
+    print("config1: qzeros[0,0] =", hex(q.qzeros[0, 0].item()))
+
+
+def gen_gptq_layer():
+    """gptq.py:1111 add_batch, :1143 fasterquant, utility.py:483 quant_weight_w_scale."""
+    from neural_compressor.torch.algorithms.weight_only.gptq import GPTQ
+    from neural_compressor.torch.algorithms.weight_only.utility import quant_weight_w_scale
+
+    g = torch.Generator().manual_seed(21)
+    N, C, T, S = 48, 256, 64, 6
+    lin = torch.nn.Linear(C, N, bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(N, C, generator=g) * 0.05)
+    X = [torch.randn(1, T, C, generator=g) for _ in range(S)]
+    for x in X:
+        x[..., 3] *= 6.0     # an outlier channel
+        x[..., 17] = 0.0     # a dead channel (diag(H) == 0, gptq.py:1189-1191)
+    out = dict(W=lin.weight.detach().clone(), X=X, runs=[])
+    variants = [
+        dict(bits=4, sym=True, group_size=128, blocksize=128, act_order=False, mse=False),
+        dict(bits=4, sym=False, group_size=128, blocksize=128, act_order=False, mse=False),
+        dict(bits=4, sym=True, group_size=128, blocksize=256, act_order=False, mse=False),   # one block: no lazy GEMM
+        dict(bits=4, sym=True, group_size=128, blocksize=2048, act_order=False, mse=False),  # config default, stale find_params
+        dict(bits=4, sym=False, group_size=32, blocksize=128, act_order=False, mse=False),
+        dict(bits=4, sym=True, group_size=32, blocksize=128, act_order=True, mse=False),
+        dict(bits=4, sym=False, group_size=128, blocksize=128, act_order=False, mse=True),
+        dict(bits=8, sym=True, group_size=128, blocksize=128, act_order=False, mse=False),
+        dict(bits=4, sym=True, group_size=-1, blocksize=128, act_order=False, mse=False),
+    ]
+    for v in variants:
+        gp = GPTQ(lin, lin.weight.data.clone(), "cpu")
+        gp.quantizer.configure(dict(dtype="int", bits=v["bits"], sym=v["sym"], group_size=v["group_size"],
+                                    mse=v["mse"], perchannel=True, use_double_quant=False, double_quant_sym=False))
+        for x in X:
+            gp.add_batch(x, None)
+        H = gp.H.clone()
+        # replay the prologue to record Hinv (gptq.py:1189-1231) without touching the reference
+        Hd = H.clone()
+        dead = torch.diag(Hd) == 0
+        Hd[dead, dead] = 1
+        perm = torch.argsort(torch.diag(Hd), descending=True) if v["act_order"] else None
+        if perm is not None:
+            Hd = Hd[perm][:, perm]
+        damp = 0.01 * torch.mean(torch.diag(Hd))
+        Hd[torch.arange(C), torch.arange(C)] += damp
+        Hinv = torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(Hd)), upper=True)
+        scale, _, zero, Q = gp.fasterquant(lin.weight.data.clone(), blocksize=v["blocksize"], percdamp=0.01,
+                                           groupsize=v["group_size"], act_order=v["act_order"])
+        Qe = Q.clone()
+        if perm is not None:
+            Qe.copy_(Qe[:, perm])
+        codes = quant_weight_w_scale(Qe, scale, None, None if v["sym"] else zero, v["group_size"], dtype="int")
+        if perm is not None:
+            codes.copy_(codes[:, torch.argsort(perm)])
+        key = "Hinv_actorder" if v["act_order"] else "Hinv"
+        out.setdefault("H", H)          # identical for every variant (same X)
+        out.setdefault(key, Hinv)       # depends only on act_order
+        assert torch.equal(out["H"], H) and torch.equal(out[key], Hinv)
+        out["runs"].append(dict(cfg=v, hinv_key=key, scale=scale.clone(), zero=zero.clone(), Q=Q.clone(),
+                                codes=codes.to(torch.int8), perm=perm))
+    torch.save(out, os.path.join(OUT, "gptq_layer.pt"))
+    print("gptq_layer:", len(out["runs"]), "runs")
+
+
+def gen_awq_module():
+    """awq.py:131-154 stats; search loops restated per module against `quant_tensor`."""
+    from neural_compressor.torch.algorithms.weight_only.awq import _get_act_scale, _get_weight_scale
+    from neural_compressor.torch.algorithms.weight_only.utility import quant_tensor
+
+    g = torch.Generator().manual_seed(31)
+    N, K = 64, 128
+    W = torch.randn(N, K, generator=g) * 0.05
+    W[:, 9] *= 5
+    b = torch.randn(N, generator=g) * 0.1
+    X = [torch.randn(1, 24, K, generator=g) * (1 + 3 * (torch.arange(K) % 16 == 0)) for _ in range(5)]
+    w_max = _get_weight_scale(W, q_group_size=32)
+    x_max = _get_act_scale(X)
+    lin = torch.nn.functional.linear
+    org = [lin(x, W, b) for x in X]
+    hist, cands = [], []
+    for i in range(20):
+        ratio = i / 20
+        s = (x_max.pow(ratio) / w_max.pow(1 - ratio)).clamp(min=1e-4).view(-1)
+        s = s / (s.max() * s.min()).sqrt()
+        wq = quant_tensor(W.mul(s.view(1, -1)), group_size=32, scheme="asym", full_range=False) / s.view(1, -1)
+        hist.append(sum((o - lin(x, wq, b)).float().pow(2).mean().item() for o, x in zip(org, X)))
+        cands.append(s)
+    chist = []
+    for i in range(10):
+        ratio = 1 - i / 100
+        wq = quant_tensor(W.clone(), group_size=32, scheme="asym", full_range=False, quantile=ratio)
+        chist.append(sum((o - lin(x, wq, b)).float().pow(2).mean().item() for o, x in zip(org, X)))
+    torch.save(dict(W=W, bias=b, X=X, w_max=w_max, x_max=x_max, scale_hist=hist, scale_cands=torch.stack(cands),
+                    clip_hist=chist), os.path.join(OUT, "awq_module.pt"))
+    print("awq_module: best scale idx", min(range(20), key=lambda i: hist[i]), "best clip idx",
+          min(range(10), key=lambda i: chist[i]))
+
+
+def gen_e2e():
+    """Public API end to end on a tiny random-init Llama: RTN / GPTQ / AWQ (quantize.py:138-325)."""
+    from neural_compressor.torch.quantization import AWQConfig, GPTQConfig, RTNConfig, convert, prepare, quantize
+
+    ids = calib_ids()
+
+    def run_fn(model):
+        for x in ids:
+            model(x)
+
+    base = tiny_llama()
+    out = dict(init_state={k: v.clone() for k, v in base.state_dict().items()}, ids=ids)
+    probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
+    out["probe"] = probe
+    with torch.no_grad():
+        out["fp_logits"] = base(probe).logits.clone()
+
+    m = tiny_llama()
+    m = convert(prepare(m, RTNConfig(bits=4, group_size=32, use_sym=True, use_layer_wise=False)))
+    with torch.no_grad():
+        out["rtn"] = dict(state=woq_state(m), logits=m(probe).logits.clone())
+
+    m = tiny_llama()
+    m = convert(prepare(m, RTNConfig(bits=4, group_size=32, use_sym=False, use_layer_wise=False)))
+    with torch.no_grad():
+        out["rtn_asym"] = dict(state=woq_state(m), logits=m(probe).logits.clone())
+
+    for tag, kw in (("gptq", dict(use_sym=True, block_size=128)), ("gptq_asym", dict(use_sym=False, block_size=128)),
+                    ("gptq_bs2048", dict(use_sym=True))):
+        m = tiny_llama()
+        cfg = GPTQConfig(bits=4, group_size=32, model_path="/tmp", **kw)
+        m = prepare(m, cfg)
+        run_fn(m)
+        m = convert(m)
+        with torch.no_grad():
+            out[tag] = dict(state=woq_state(m), logits=m(probe).logits.clone())
+
+    m = tiny_llama()
+    cfg = AWQConfig(bits=4, group_size=32, use_sym=False)
+    m = quantize(m, cfg, run_fn=run_fn, example_inputs=ids[0])
+    with torch.no_grad():
+        st = {k: v.clone() for k, v in m.state_dict().items()}
+        out["awq"] = dict(state=st, logits=m(probe).logits.clone(),
+                          module_types={n: type(x).__name__ for n, x in m.named_modules()})
+    torch.save(out, os.path.join(OUT, "e2e_tiny_llama.pt"))
+    print("e2e: keys", [k for k in out if k not in ("init_state",)])
+
+
+if __name__ == "__main__":
+    load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    which = sys.argv[1:] or ["rtn", "config1", "gptq", "awq", "e2e"]
+    with torch.no_grad():
+        if "rtn" in which:
+            gen_rtn_pack()
+        if "config1" in which:
+            gen_config1()
+        if "gptq" in which:
+            gen_gptq_layer()
+        if "awq" in which:
+            gen_awq_module()
+        if "e2e" in which:
+            gen_e2e()

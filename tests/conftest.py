@@ -1,0 +1,53 @@
+"""pytest configuration: the `gpu` marker and shared fixtures."""
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN, name), weights_only=False)
+
+
+@pytest.fixture(scope="session")
+def golden_rtn():
+    return load_golden("rtn_pack.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_gptq():
+    return load_golden("gptq_layer.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_awq():
+    return load_golden("awq_module.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_config1():
+    return load_golden("config1_rtn_linear1024.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_e2e():
+    return load_golden("e2e_tiny_llama.pt")
