@@ -1,0 +1,539 @@
+// woq_gemm.cu -- K6: INCWeightOnlyLinear.forward as ONE fused kernel (unpack + dequant + matmul).
+//
+// Reference: modules.py:594-610 forward, :413-443 recover, :377-411 unpack.  The reference de-quantises
+// the whole weight once (fp16( int8(q - zp) * scale_fp16 )), caches it as fp32 and calls F.linear; here
+// the packed words are streamed from HBM exactly once per call and never materialised as fp weights.
+//
+// Layout (optimum format): qweight int32 [K/n_pack, N] -- field e of word (kw, n) is the code of
+// W[n, kw*n_pack + e]; consecutive n are contiguous, so a warp reading 128 B-512 B segments of one kw
+// row is fully coalesced.  scales fp16 [G, N], qzeros int32 [G, N/n_pack] (stored zp-1).
+//
+// Fast path (bits 4/8, no g_idx, N % 32 == 0, group % (4*k_per_word) == 0): batch M <= 64 is HBM-bound
+// (ridge at M ~ 70), so the design goal is bytes in flight, not flops:
+//   * every lane keeps D = 8 independent 16-byte ld.global.nc (L1::no_allocate) loads in flight,
+//     16 warps/SM -> 64 KB/SM outstanding;
+//   * the 4-bit -> fp16 conversion uses the 0x6400 magic-number trick (2 LOP3 + 1 SHF per 4 codes, exact
+//     subtraction of 1024+zp in half2), and the multiply-accumulate runs on the tensor cores through
+//     mma.sync.m16n8k16 with the out-channel dimension as the MMA "M" (16 rows = 4 lanes-groups x 4 n) and
+//     the batch as the MMA "N" (8 columns), so CUDA-core issue slots are spent only on the dequant;
+//   * k is consumed in a permuted order (the dot product is permutation invariant): lane t of a quad
+//     owns qweight row kw0+t, so one 16-byte load feeds 4 MMAs without any shuffles; x is staged once per
+//     CTA into shared memory in the matching permuted order;
+//   * M <= 8: group scale applied after the per-group accumulation in fp32 (POST mode, 9 ALU ops/word);
+//     M  > 8: scale applied in half2 before the MMA, reproducing the reference's fp16 weight exactly;
+//   * split-K across CTAs with a deterministic "last CTA reduces" epilogue (fixed summation order).
+// The general path (g_idx / ragged shapes / other bit widths) is a plain CUDA-core kernel.
+#include "common.cuh"
+
+namespace b200woq {
+
+struct GemmParams {
+  const void* x;
+  int x_dtype;
+  int64_t M, K, N;  // M = rows of this chunk (<= 64 on the fast path)
+  const int32_t* qweight;
+  const int32_t* qzeros;
+  const __half* scales;
+  const int32_t* g_idx;
+  const void* bias;
+  int bias_dtype;
+  const float* input_scale;
+  void* y;
+  int y_dtype;
+  int bits, g;
+  int64_t G;
+  int S;  // split-K factor
+  float* ws_partial;
+  int* ws_counter;
+  int xs_ld;  // halves per smem x row
+  int pdl;
+};
+
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, int64_t i) {
+  if (dtype == B200WOQ_F32) return ((const float*)p)[i];
+  if (dtype == B200WOQ_F16) return __half2float(((const __half*)p)[i]);
+  return __bfloat162float(((const __nv_bfloat16*)p)[i]);
+}
+__device__ __forceinline__ void store_from_float(void* p, int dtype, int64_t i, float v) {
+  if (dtype == B200WOQ_F32)
+    ((float*)p)[i] = v;
+  else if (dtype == B200WOQ_F16)
+    ((__half*)p)[i] = __float2half_rn(v);
+  else
+    ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ int4 ldg_nc_v4(const int32_t* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+constexpr int kPrefetch = 8;  // 16-byte loads in flight per lane
+
+// BITS = 4: word -> P0=(c0,c4) P1=(c1,c5) P2=(c2,c6) P3=(c3,c7) as half2 of (code - zp)
+// BITS = 8: word -> P0=(c0,c2) P1=(c1,c3)
+template <int BITS>
+struct Dequant;
+
+template <>
+struct Dequant<4> {
+  static constexpr int kPairs = 4;
+  // zc = half2(1024 + zp), zn = half2(-(64 + zp))
+  static __device__ __forceinline__ void run(uint32_t w, __half2 zc, __half2 zn, __half2 (&P)[4]) {
+    const __half2 sixteenth = __float2half2_rn(0.0625f);
+    const uint32_t w8 = w >> 8;
+    P[0] = __hsub2(u32_as_h2((w & 0x000f000fu) | 0x64006400u), zc);
+    P[1] = __hfma2(u32_as_h2((w & 0x00f000f0u) | 0x64006400u), sixteenth, zn);
+    P[2] = __hsub2(u32_as_h2((w8 & 0x000f000fu) | 0x64006400u), zc);
+    P[3] = __hfma2(u32_as_h2((w8 & 0x00f000f0u) | 0x64006400u), sixteenth, zn);
+  }
+};
+
+template <>
+struct Dequant<8> {
+  static constexpr int kPairs = 2;
+  static __device__ __forceinline__ void run(uint32_t w, __half2 zc, __half2 /*zn*/, __half2 (&P)[4]) {
+    P[0] = __hsub2(u32_as_h2((w & 0x00ff00ffu) | 0x64006400u), zc);
+    P[1] = __hsub2(u32_as_h2(((w >> 8) & 0x00ff00ffu) | 0x64006400u), zc);
+    // .to(torch.int8) in recover() wraps q - zp into [-128, 127] (modules.py:435)
+    const __half2 hi = __float2half2_rn(127.f), lo = __float2half2_rn(-128.f), wrap = __float2half2_rn(256.f);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      P[i] = __hsub2(P[i], __hmul2(__hgt2(P[i], hi), wrap));
+      P[i] = __hadd2(P[i], __hmul2(__hlt2(P[i], lo), wrap));
+    }
+  }
+};
+
+template <int BITS, int MT, bool POST>
+__global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(const GemmParams p) {
+  constexpr int KPW = 32 / BITS;   // codes per word
+  constexpr int KSTEP = 4 * KPW;   // k covered by the 4 quad-lanes' words
+  constexpr int NSTEP = (BITS == 4) ? 2 : 1;  // MMA k16 steps per 16-byte load
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __half* xs = reinterpret_cast<__half*>(smem_raw);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int strip = warp & 3, khalf = warp >> 2;
+  const int64_t N = p.N;
+  const int64_t n_strip = (int64_t)blockIdx.x * 128 + strip * 32;
+  const int64_t n0 = n_strip + 4 * gq;
+  const bool strip_valid = n_strip < N;
+  const int g = p.g;
+  const int NI = g / KSTEP;  // 16-byte loads per group per lane
+
+  // CTA group range and this warp's half of it
+  const int gb = (int)((int64_t)blockIdx.y * p.G / p.S), ge = (int)(((int64_t)blockIdx.y + 1) * p.G / p.S);
+  const int gmid = gb + (ge - gb + 1) / 2;
+  const int g0 = khalf == 0 ? gb : gmid, g1 = khalf == 0 ? gmid : ge;
+  const int total = strip_valid ? (g1 - g0) * NI : 0;
+
+  // word row of iteration `it` is g0*g/KPW + 4*it + t: groups are contiguous in k, so the pointer simply
+  // advances by 4 rows per iteration across group boundaries
+  const int32_t* wptr = p.qweight + ((int64_t)g0 * (g / KPW) + t) * N + n0;
+  const int64_t wstep = 4 * N;
+
+  // weights do not depend on the previous kernel: start streaming them before the PDL wait
+  int4 buf[kPrefetch];
+#pragma unroll
+  for (int j = 0; j < kPrefetch; ++j)
+    if (j < total) buf[j] = ldg_nc_v4(wptr + (int64_t)j * wstep);
+  wptr += (int64_t)kPrefetch * wstep;
+
+  if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // stage x (permuted, fp16, optional MulLinear input scale) for the CTA's k range
+  {
+    const int64_t kbase = (int64_t)gb * g;
+    const int ksz = (ge - gb) * g;
+    const int cnt = (int)p.M * ksz;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int m = i / ksz, kk = i - m * ksz;
+      float v = load_as_float(p.x, p.x_dtype, (int64_t)m * p.K + kbase + kk);
+      if (p.input_scale) v *= p.input_scale[kbase + kk];
+      const int e = kk % KPW;
+      const int pos = (BITS == 4) ? ((e & 3) * 2 + (e >> 2)) : ((e & 1) * 2 + (e >> 1));
+      xs[m * p.xs_ld + (kk - e) + pos] = __float2half_rn(v);
+    }
+  }
+  __syncthreads();
+
+  float acc[2][MT][4];
+  float accg[2][MT][4];  // POST only: per-group partial sums (dead code otherwise)
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < MT; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc[a][b][c] = 0.f;
+        accg[a][b][c] = 0.f;
+      }
+
+  // per-group constants for the lane's 4 out-channels (current + prefetched next)
+  uint2 sc_cur = make_uint2(0, 0), sc_nxt = make_uint2(0, 0);
+  uint32_t zw_cur = 0, zw_nxt = 0;
+  const int64_t Nw = (N + KPW - 1) / KPW;
+  const int zshift = (BITS == 4) ? (int)((n0 & 7) * 4) : 0;
+  auto load_group_consts = [&](int gi, uint2& sc, uint32_t& zw) {
+    sc = *reinterpret_cast<const uint2*>(p.scales + (int64_t)gi * N + n0);
+    zw = ((uint32_t)p.qzeros[(int64_t)gi * Nw + n0 / KPW]) >> zshift;
+  };
+  if (total > 0) load_group_consts(g0, sc_nxt, zw_nxt);
+
+  __half2 zc[4], zn[4], sh[4];
+  float sf[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    zc[r] = zn[r] = sh[r] = __float2half2_rn(0.f);
+    sf[r] = 0.f;
+  }
+  int i_in_g = 0, gi = g0;
+  int xoff = (g0 - gb) * g + t * KPW;  // halves; advances by 4*KPW per iteration
+
+  for (int base = 0; base < total; base += kPrefetch) {
+#pragma unroll
+    for (int j = 0; j < kPrefetch; ++j) {
+      const int it = base + j;
+      if (it < total) {
+        const int4 wv = buf[j];
+        if (it + kPrefetch < total) buf[j] = ldg_nc_v4(wptr);
+        wptr += wstep;
+        if (i_in_g == 0) {
+          sc_cur = sc_nxt;
+          zw_cur = zw_nxt;
+          if (gi + 1 < g1) load_group_consts(gi + 1, sc_nxt, zw_nxt);
+          const __half2 s01 = u32_as_h2(sc_cur.x), s23 = u32_as_h2(sc_cur.y);
+          const __half sr[4] = {__low2half(s01), __high2half(s01), __low2half(s23), __high2half(s23)};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            uint32_t z = ((zw_cur >> (BITS * r)) & ((1u << BITS) - 1u)) + 1u;  // stored zp-1 (modules.py:363)
+            if (z > ((1u << BITS) - 1u)) z = 0;                                  // modules.py:409-410
+            zc[r] = __float2half2_rn(1024.f + (float)z);
+            zn[r] = __float2half2_rn(-(64.f + (float)z));
+            sh[r] = __half2half2(sr[r]);
+            sf[r] = __half2float(sr[r]);
+          }
+        }
+        __half2 P[4][4];
+        Dequant<BITS>::run((uint32_t)wv.x, zc[0], zn[0], P[0]);
+        Dequant<BITS>::run((uint32_t)wv.y, zc[1], zn[1], P[1]);
+        Dequant<BITS>::run((uint32_t)wv.z, zc[2], zn[2], P[2]);
+        Dequant<BITS>::run((uint32_t)wv.w, zc[3], zn[3], P[3]);
+        if (!POST) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int q = 0; q < Dequant<BITS>::kPairs; ++q) P[r][q] = __hmul2(P[r][q], sh[r]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int m = gq + 8 * mt;
+          uint32_t xb[4] = {0u, 0u, 0u, 0u};
+          if (m < p.M) {
+            if (BITS == 4) {
+              const uint4 v = *reinterpret_cast<const uint4*>(xs + m * p.xs_ld + xoff);
+              xb[0] = v.x; xb[1] = v.y; xb[2] = v.z; xb[3] = v.w;
+            } else {
+              const uint2 v = *reinterpret_cast<const uint2*>(xs + m * p.xs_ld + xoff);
+              xb[0] = v.x; xb[1] = v.y;
+            }
+          }
+#pragma unroll
+          for (int st = 0; st < NSTEP; ++st) {
+            if (POST) {
+              mma_16816(accg[0][mt], h2_as_u32(P[0][2 * st]), h2_as_u32(P[1][2 * st]), h2_as_u32(P[0][2 * st + 1]),
+                        h2_as_u32(P[1][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
+              mma_16816(accg[1][mt], h2_as_u32(P[2][2 * st]), h2_as_u32(P[3][2 * st]), h2_as_u32(P[2][2 * st + 1]),
+                        h2_as_u32(P[3][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
+            } else {
+              mma_16816(acc[0][mt], h2_as_u32(P[0][2 * st]), h2_as_u32(P[1][2 * st]), h2_as_u32(P[0][2 * st + 1]),
+                        h2_as_u32(P[1][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
+              mma_16816(acc[1][mt], h2_as_u32(P[2][2 * st]), h2_as_u32(P[3][2 * st]), h2_as_u32(P[2][2 * st + 1]),
+                        h2_as_u32(P[3][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
+            }
+          }
+        }
+        xoff += 4 * KPW;
+        if (++i_in_g == NI) {
+          i_in_g = 0;
+          ++gi;
+          if (POST) {
+#pragma unroll
+            for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                acc[tile][mt][0] = fmaf(accg[tile][mt][0], sf[2 * tile], acc[tile][mt][0]);
+                acc[tile][mt][1] = fmaf(accg[tile][mt][1], sf[2 * tile], acc[tile][mt][1]);
+                acc[tile][mt][2] = fmaf(accg[tile][mt][2], sf[2 * tile + 1], acc[tile][mt][2]);
+                acc[tile][mt][3] = fmaf(accg[tile][mt][3], sf[2 * tile + 1], acc[tile][mt][3]);
+                accg[tile][mt][0] = accg[tile][mt][1] = accg[tile][mt][2] = accg[tile][mt][3] = 0.f;
+              }
+          }
+        }
+      }
+    }
+  }
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // ---- epilogue: lane holds y[m = 8mt + 2t + {0,1}][n0 + {0,1,2,3}] ----
+  // acc[tile][mt][c]: c0,c1 -> row gq (n0 + 2*tile), cols 2t,2t+1 ; c2,c3 -> row gq+8 (n0 + 2*tile + 1)
+  __syncthreads();  // xs no longer needed; reuse smem for the k-half reduction
+  float* red = reinterpret_cast<float*>(smem_raw);  // [4 strips][MT][32 lanes][8]
+  if (khalf == 1) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      float* dst = red + (((strip * MT + mt) * 32 + lane) * 8);
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[tile * 4 + c] = acc[tile][mt][c];
+    }
+  }
+  __syncthreads();
+  if (khalf == 0 && strip_valid) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const float* src = red + (((strip * MT + mt) * 32 + lane) * 8);
+#pragma unroll
+      for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[tile][mt][c] += src[tile * 4 + c];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int m = 8 * mt + 2 * t + half;
+        if (m < p.M) {
+          // n0+0: tile0 c(half) ; n0+1: tile0 c(2+half) ; n0+2: tile1 c(half) ; n0+3: tile1 c(2+half)
+          float4 v = make_float4(acc[0][mt][half], acc[0][mt][2 + half], acc[1][mt][half], acc[1][mt][2 + half]);
+          if (p.S == 1) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              float o = (&v.x)[r];
+              if (p.bias) o += load_as_float(p.bias, p.bias_dtype, n0 + r);
+              store_from_float(p.y, p.y_dtype, (int64_t)m * N + n0 + r, o);
+            }
+          } else {
+            *reinterpret_cast<float4*>(p.ws_partial + ((int64_t)blockIdx.y * p.M + m) * N + n0) = v;
+          }
+        }
+      }
+    }
+  }
+  if (p.S > 1) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int old = atomicAdd(p.ws_counter + blockIdx.x, 1);
+      is_last = (old == p.S - 1);
+      if (is_last) p.ws_counter[blockIdx.x] = 0;  // leave the workspace zeroed for the next call
+    }
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      const int64_t nt0 = (int64_t)blockIdx.x * 128;
+      for (int i = threadIdx.x; i < p.M * 128; i += blockDim.x) {
+        const int m = i / 128;
+        const int64_t n = nt0 + (i % 128);
+        if (n < N) {
+          float s = 0.f;
+          for (int sp = 0; sp < p.S; ++sp) s += __ldcg(p.ws_partial + ((int64_t)sp * p.M + m) * N + n);
+          if (p.bias) s += load_as_float(p.bias, p.bias_dtype, n);
+          store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, s);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// general path: any bits in [1,8], g_idx, ragged K / group.  32 lanes <-> 32 out-channels, 8 warps split K,
+// 8 batch rows per CTA.y.  Weight value = fp16(int8(q - zp) * scale) exactly as recover() computes it.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) woq_gemm_general_kernel(const GemmParams p) {
+  __shared__ float red[8][8][33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t m0 = (int64_t)blockIdx.y * 8;
+  const int n_pack = 32 / p.bits;
+  const uint32_t mask = (1u << p.bits) - 1u;
+  const int64_t Kw = (p.K + n_pack - 1) / n_pack, Nw = (p.N + n_pack - 1) / n_pack;
+  const int64_t per = (Kw + 7) / 8;
+  const int64_t kw_begin = warp * per, kw_end = (kw_begin + per < Kw) ? kw_begin + per : Kw;
+  float acc[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) acc[m] = 0.f;
+  if (n < p.N) {
+    for (int64_t kw = kw_begin; kw < kw_end; ++kw) {
+      const uint32_t word = (uint32_t)p.qweight[kw * p.N + n];
+      for (int e = 0; e < n_pack; ++e) {
+        const int64_t k = kw * n_pack + e;
+        if (k >= p.K) break;
+        const int64_t gi = p.g_idx ? p.g_idx[k] : k / p.g;
+        const uint32_t zw = (uint32_t)p.qzeros[gi * Nw + n / n_pack];
+        uint32_t z = ((zw >> (p.bits * (n % n_pack))) & mask) + 1u;
+        if (z > mask) z = 0;
+        const int8_t d = (int8_t)((int)((word >> (p.bits * e)) & mask) - (int)z);
+        const float wv = __half2float(__hmul(__int2half_rn((int)d), p.scales[gi * p.N + n]));
+        const float is = p.input_scale ? p.input_scale[k] : 1.f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+          if (m0 + m < p.M) acc[m] = fmaf(load_as_float(p.x, p.x_dtype, (m0 + m) * p.K + k) * is, wv, acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) red[warp][m][lane] = acc[m];
+  __syncthreads();
+  if (warp == 0 && n < p.N) {
+    for (int m = 0; m < 8 && m0 + m < p.M; ++m) {
+      float s = 0.f;
+      for (int w = 0; w < 8; ++w) s += red[w][m][lane];
+      if (p.bias) s += load_as_float(p.bias, p.bias_dtype, n);
+      store_from_float(p.y, p.y_dtype, (m0 + m) * p.N + n, s);
+    }
+  }
+}
+
+static bool fast_path_ok(int64_t N, int64_t K, int bits, int g, const int32_t* g_idx) {
+  if (g_idx) return false;
+  if (bits != 4 && bits != 8) return false;
+  const int kstep = 4 * (32 / bits);
+  return (N % 32 == 0) && (g % kstep == 0) && (K % g == 0);
+}
+
+// split-K factor: enough CTAs for >= 2 per SM, x tile must fit in shared memory
+static int choose_split(int64_t M, int64_t N, int64_t K, int g) {
+  const int64_t n_tiles = ceil_div(N, 128);
+  const int64_t G = K / g;
+  const int64_t want = 3 * (int64_t)num_sms();
+  int64_t S = ceil_div(want, n_tiles);
+  if (S > G / 2) S = G / 2;  // at least one group per k-half
+  if (S < 1) S = 1;
+  // shared-memory cap: M * (ceil(G/S)*g + 32) halves <= 96 KB
+  while (S < G && M * (ceil_div(G, S) * g + 32) * 2 > 96 * 1024) ++S;
+  return (int)S;
+}
+
+}  // namespace b200woq
+
+using namespace b200woq;
+
+extern "C" int64_t b200woq_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size) {
+  const int g = eff_group(K, group_size);
+  const int64_t Mc = M < 64 ? M : 64;
+  // upper bound over any split factor we may pick (S <= G): partial sums + one counter per n tile
+  const int64_t G = ceil_div(K, g);
+  int64_t S = choose_split(Mc, N, K, g);
+  if (S > G) S = G;
+  return S * Mc * N * (int64_t)sizeof(float) + ((ceil_div(N, 128) * (int64_t)sizeof(int) + 255) / 256) * 256 + 256;
+}
+
+template <int BITS>
+static int launch_fast(GemmParams& p, int64_t Mc, cudaStream_t st) {
+  const int mt = Mc <= 8 ? 1 : Mc <= 16 ? 2 : Mc <= 32 ? 4 : 8;
+  const int64_t gmax = ceil_div(p.G, p.S);
+  p.xs_ld = (int)(gmax * p.g + 32);
+  size_t smem = (size_t)Mc * p.xs_ld * sizeof(__half);
+  const size_t red = (size_t)4 * mt * 32 * 8 * sizeof(float);
+  if (smem < red) smem = red;
+  dim3 grid((unsigned)ceil_div(p.N, 128), (unsigned)p.S);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+#define WOQ_LAUNCH(MT_, POST_)                                                                              \
+  do {                                                                                                      \
+    auto kern = woq_gemm_mma_kernel<BITS, MT_, POST_>;                                                      \
+    if (smem > 48 * 1024) WOQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    WOQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));                                                            \
+  } while (0)
+  switch (mt) {
+    case 1: WOQ_LAUNCH(1, true); break;
+    case 2: WOQ_LAUNCH(2, false); break;
+    case 4: WOQ_LAUNCH(4, false); break;
+    default: WOQ_LAUNCH(8, false); break;
+  }
+#undef WOQ_LAUNCH
+  return 0;
+}
+
+extern "C" int b200woq_linear_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N,
+                                      const int32_t* qweight, const int32_t* qzeros, const void* scales16,
+                                      const int32_t* g_idx, const void* bias, int bias_dtype,
+                                      const float* input_scale, void* y, int y_dtype, int bits, int group_size,
+                                      void* workspace, int64_t workspace_bytes, int flags, void* stream) {
+  WOQ_CHECK_ARG(x && qweight && qzeros && scales16 && y, "linear_forward: null pointer");
+  WOQ_CHECK_ARG(M > 0 && K > 0 && N > 0, "linear_forward: empty shape");
+  WOQ_CHECK_ARG(bits >= 1 && bits <= 8, "linear_forward: bits must be in [1,8]");
+  WOQ_CHECK_ARG(x_dtype >= 0 && x_dtype <= 2 && y_dtype >= 0 && y_dtype <= 2, "linear_forward: bad dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = eff_group(K, group_size);
+  GemmParams p = {};
+  p.x_dtype = x_dtype;
+  p.K = K;
+  p.N = N;
+  p.qweight = qweight;
+  p.qzeros = qzeros;
+  p.scales = (const __half*)scales16;
+  p.g_idx = g_idx;
+  p.bias = bias;
+  p.bias_dtype = bias_dtype;
+  p.input_scale = input_scale;
+  p.y_dtype = y_dtype;
+  p.bits = bits;
+  p.g = g;
+  p.G = ceil_div(K, g);
+  p.pdl = (flags & 2) ? 1 : 0;
+  const size_t xes = x_dtype == B200WOQ_F32 ? 4 : 2, yes = y_dtype == B200WOQ_F32 ? 4 : 2;
+  const bool fast = !(flags & 1) && fast_path_ok(N, K, bits, g, g_idx);
+  if (!fast) {
+    p.x = x;
+    p.y = y;
+    p.M = M;
+    dim3 grid((unsigned)ceil_div(N, 32), (unsigned)ceil_div(M, 8));
+    woq_gemm_general_kernel<<<grid, 256, 0, st>>>(p);
+    WOQ_LAUNCH_CHECK();
+    return 0;
+  }
+  for (int64_t m0 = 0; m0 < M; m0 += 64) {
+    const int64_t Mc = (M - m0) < 64 ? (M - m0) : 64;
+    p.x = (const char*)x + (size_t)m0 * K * xes;
+    p.y = (char*)y + (size_t)m0 * N * yes;
+    p.M = Mc;
+    p.S = choose_split(Mc, N, K, g);
+    if (p.S > 1) {
+      const int64_t need = (int64_t)p.S * Mc * N * (int64_t)sizeof(float) + ((ceil_div(N, 128) * (int64_t)sizeof(int) + 255) / 256) * 256;
+      if (!workspace || workspace_bytes < need) {
+        set_error("linear_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
+        return B200WOQ_EWORKSPACE;
+      }
+      p.ws_counter = (int*)workspace;  // counters first (must stay zero between calls)
+      p.ws_partial = (float*)((char*)workspace + ((ceil_div(N, 128) * sizeof(int) + 255) / 256) * 256);
+    }
+    int rc = (bits == 4) ? launch_fast<4>(p, Mc, st) : launch_fast<8>(p, Mc, st);
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -1,0 +1,240 @@
+"""Tensor-level wrappers over the C ABI (include/b200woq.h).
+
+PyTorch is plumbing here: it owns device memory and the current stream; every computation below is a
+hand-written sm_100a kernel inside libb200woq.so.  All inputs must be contiguous CUDA tensors -- there
+is no CPU path and no fallback.
+"""
+from __future__ import annotations
+
+import math
+from ctypes import c_void_p
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, dt, ptr, require_cuda, stream_ptr
+
+
+def _eff_group(K: int, group_size: int) -> int:
+    return K if (group_size <= 0 or group_size > K) else group_size
+
+
+def n_pack(bits: int) -> int:
+    return 32 // bits
+
+
+# ------------------------------------------------------------------ K4: RTN + pack
+def rtn_params(W: torch.Tensor, bits=4, group_size=-1, sym=False, full_range=False, quantile=1.0):
+    """quant_tensor()'s per-group (scale, zp) -- fp32 [N, G] (utility.py:162-244)."""
+    require_cuda(W, "W")
+    N, K = W.shape
+    G = math.ceil(K / _eff_group(K, group_size))
+    scale = torch.empty((N, G), dtype=torch.float32, device=W.device)
+    zp = None if sym else torch.empty((N, G), dtype=torch.float32, device=W.device)
+    check(_lib.load().b200woq_rtn_params(ptr(W), dt(W), N, K, bits, group_size, int(sym), int(full_range),
+                                         float(quantile), ptr(scale), ptr(zp), stream_ptr(W.device)), "rtn_params")
+    return scale, zp
+
+
+def pack_params(scale: torch.Tensor, zp: Optional[torch.Tensor], bits: int):
+    """scales fp16 [G,N], qzeros int32 [G, ceil(N/n_pack)] (modules.py:345-371)."""
+    require_cuda(scale, "scale")
+    N, G = scale.shape
+    scale = scale.float().contiguous()
+    zp = None if zp is None else zp.float().contiguous()
+    scales16 = torch.empty((G, N), dtype=torch.float16, device=scale.device)
+    qzeros = torch.empty((G, math.ceil(N / n_pack(bits))), dtype=torch.int32, device=scale.device)
+    check(_lib.load().b200woq_pack_params(ptr(scale), ptr(zp), N, G, bits, ptr(scales16), ptr(qzeros),
+                                          stream_ptr(scale.device)), "pack_params")
+    return scales16, qzeros
+
+
+def rtn_quant_pack(W: torch.Tensor, bits=4, group_size=-1, sym=False, full_range=False, quantile=1.0,
+                   return_codes=False):
+    """quant_tensor(return_int=True) + INCWeightOnlyLinear.pack.  Returns dict(qweight, qzeros, scales,
+    scale_f32, zp_f32[, codes])."""
+    require_cuda(W, "W")
+    N, K = W.shape
+    scale, zp = rtn_params(W, bits, group_size, sym, full_range, quantile)
+    qweight = torch.empty((math.ceil(K / n_pack(bits)), N), dtype=torch.int32, device=W.device)
+    codes = torch.empty((N, K), dtype=torch.uint8, device=W.device) if return_codes else None
+    check(_lib.load().b200woq_rtn_quant_pack(ptr(W), dt(W), N, K, bits, group_size, int(sym), ptr(scale), ptr(zp),
+                                             ptr(qweight), ptr(codes), stream_ptr(W.device)), "rtn_quant_pack")
+    scales16, qzeros = pack_params(scale, zp, bits)
+    out = dict(qweight=qweight, qzeros=qzeros, scales=scales16, scale_f32=scale, zp_f32=zp)
+    if return_codes:
+        out["codes"] = codes
+    return out
+
+
+def rtn_fake_quant(W: torch.Tensor, bits=4, group_size=-1, sym=False, full_range=False, quantile=1.0,
+                   col_scale: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    """quant_tensor(return_int=False); with col_scale: qdq(W*s)/s (awq.py:326-335)."""
+    require_cuda(W, "W")
+    N, K = W.shape
+    if out is None:
+        out = torch.empty_like(W)
+    if col_scale is not None:
+        col_scale = col_scale.float().contiguous()
+    check(_lib.load().b200woq_rtn_fake_quant(ptr(W), dt(W), N, K, bits, group_size, int(sym), int(full_range),
+                                             float(quantile), ptr(col_scale), ptr(out), stream_ptr(W.device)),
+          "rtn_fake_quant")
+    return out
+
+
+def pack_codes(codes: torch.Tensor, bits: int):
+    require_cuda(codes, "codes")
+    assert codes.dtype == torch.uint8
+    N, K = codes.shape
+    qweight = torch.empty((math.ceil(K / n_pack(bits)), N), dtype=torch.int32, device=codes.device)
+    check(_lib.load().b200woq_pack_codes(ptr(codes), N, K, bits, ptr(qweight), stream_ptr(codes.device)), "pack_codes")
+    return qweight
+
+
+def unpack(qweight, qzeros, bits, in_features, out_features, n_groups):
+    require_cuda(qweight, "qweight")
+    codes = torch.empty((out_features, in_features), dtype=torch.uint8, device=qweight.device)
+    zps = torch.empty((out_features, n_groups), dtype=torch.uint8, device=qweight.device)
+    check(_lib.load().b200woq_unpack(ptr(qweight), ptr(qzeros), out_features, in_features, n_groups, bits, ptr(codes),
+                                     ptr(zps), stream_ptr(qweight.device)), "unpack")
+    return codes, zps
+
+
+def dequantize(qweight, qzeros, scales, bits, group_size, in_features, out_features, g_idx=None):
+    """recover(): fp16 [N,K] (modules.py:413-443)."""
+    require_cuda(qweight, "qweight")
+    out = torch.empty((out_features, in_features), dtype=torch.float16, device=qweight.device)
+    check(_lib.load().b200woq_dequantize(ptr(qweight), ptr(qzeros), ptr(scales), ptr(g_idx), out_features, in_features,
+                                         bits, group_size, ptr(out), stream_ptr(qweight.device)), "dequantize")
+    return out
+
+
+# ------------------------------------------------------------------ K6: fused dequant GEMM
+_WS_CACHE = {}
+
+
+def _workspace(device, nbytes: int) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)  # kernels keep it zeroed
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def woq_linear(x, qweight, qzeros, scales, bias, bits, group_size, in_features, out_features, g_idx=None,
+               input_scale=None, out_dtype=torch.float32, flags=0, out=None):
+    """INCWeightOnlyLinear.forward (modules.py:594-610) as one fused kernel."""
+    require_cuda(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, in_features)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    lib = _lib.load()
+    nbytes = lib.b200woq_linear_workspace_bytes(M, out_features, in_features, bits, group_size)
+    ws = _workspace(x.device, nbytes)
+    if out is None:
+        out = torch.empty((M, out_features), dtype=out_dtype, device=x.device)
+    check(lib.b200woq_linear_forward(ptr(x2), dt(x2), M, in_features, out_features, ptr(qweight), ptr(qzeros),
+                                     ptr(scales), ptr(g_idx), ptr(bias), dt(bias) if bias is not None else 0,
+                                     ptr(input_scale), ptr(out), dt(out), bits, group_size, ptr(ws), ws.numel(),
+                                     flags, stream_ptr(x.device)), "linear_forward")
+    return out.reshape(*lead, out_features)
+
+
+# ------------------------------------------------------------------ K1-K3: GPTQ
+def hessian_accumulate(X: torch.Tensor, Hsum: torch.Tensor):
+    """Hsum += X^T X (raw fp32 sums; gptq.py:1111-1141 closed form, see hessian_finalize)."""
+    require_cuda(X, "X")
+    X2 = X.reshape(-1, X.shape[-1])
+    if not X2.is_contiguous():
+        X2 = X2.contiguous()
+    T, C = X2.shape
+    assert Hsum.shape == (C, C) and Hsum.dtype == torch.float32 and Hsum.is_contiguous()
+    check(_lib.load().b200woq_hessian_accumulate(ptr(X2), dt(X2), T, C, C, ptr(Hsum), stream_ptr(X.device)),
+          "hessian_accumulate")
+
+
+def hessian_finalize(Hsum: torch.Tensor, nsamples: float, percdamp: float):
+    """In place: H = 2/n * Hsum (full symmetric), dead handling, damping.  Returns (H, dead_mask uint8[C])."""
+    require_cuda(Hsum, "Hsum")
+    C = Hsum.shape[0]
+    dead = torch.empty(C, dtype=torch.uint8, device=Hsum.device)
+    scratch = torch.empty(2, dtype=torch.float32, device=Hsum.device)
+    check(_lib.load().b200woq_hessian_finalize(ptr(Hsum), C, float(nsamples), float(percdamp), ptr(dead), ptr(scratch),
+                                               stream_ptr(Hsum.device)), "hessian_finalize")
+    return Hsum, dead
+
+
+def cholesky_inverse_upper(H: torch.Tensor) -> torch.Tensor:
+    """gptq.py:1228-1231.  Round 1: cuSOLVER through torch.linalg on the device (library call)."""
+    L = torch.linalg.cholesky(H)
+    Hi = torch.cholesky_inverse(L)
+    return torch.linalg.cholesky(Hi, upper=True).contiguous()
+
+
+def gptq_fasterquant(W: torch.Tensor, Hinv: torch.Tensor, dead_mask: Optional[torch.Tensor], blocksize=128,
+                     groupsize=-1, bits=4, sym=False, mse=False, want_q=True):
+    """GPTQ.fasterquant column loop for one layer (gptq.py:1250-1304).  W fp32 [N,C] is destroyed.
+
+    Returns dict(codes uint8 [N,C], Q fp32 [N,C] | None, scale [N,G], zero [N,G], losses [N])."""
+    require_cuda(W, "W")
+    assert W.dtype == torch.float32 and Hinv.dtype == torch.float32 and Hinv.is_contiguous()
+    N, C = W.shape
+    G = 1 if groupsize <= 0 else math.ceil(C / groupsize)
+    dev = W.device
+    codes = torch.empty((N, C), dtype=torch.uint8, device=dev)
+    Q = torch.empty((N, C), dtype=torch.float32, device=dev) if want_q else None
+    scale = torch.empty((N, G), dtype=torch.float32, device=dev)
+    zero = torch.empty((N, G), dtype=torch.float32, device=dev)
+    losses = torch.empty(N, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    nbytes = lib.b200woq_gptq_workspace_bytes(N, C, blocksize)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib.b200woq_gptq_fasterquant(ptr(W), ptr(Hinv), ptr(dead_mask), N, C, blocksize, groupsize, bits, int(sym),
+                                       1 if mse else 0, ptr(codes), ptr(Q), ptr(scale), ptr(zero), ptr(losses),
+                                       ptr(ws), nbytes, stream_ptr(dev)), "gptq_fasterquant")
+    return dict(codes=codes, Q=Q, scale=scale, zero=zero, losses=losses)
+
+
+# ------------------------------------------------------------------ K5/K7 statistics
+def awq_weight_scale(W: torch.Tensor, group_size: int) -> torch.Tensor:
+    require_cuda(W, "W")
+    N, K = W.shape
+    out = torch.empty(K, dtype=torch.float32, device=W.device)
+    check(_lib.load().b200woq_awq_weight_scale(ptr(W), dt(W), N, K, group_size, ptr(out), stream_ptr(W.device)),
+          "awq_weight_scale")
+    return out
+
+
+def abs_colsum_accumulate(X: torch.Tensor, acc: torch.Tensor):
+    require_cuda(X, "X")
+    X2 = X.reshape(-1, X.shape[-1])
+    if not X2.is_contiguous():
+        X2 = X2.contiguous()
+    T, K = X2.shape
+    check(_lib.load().b200woq_abs_colsum_accumulate(ptr(X2), dt(X2), T, K, K, ptr(acc), stream_ptr(X.device)),
+          "abs_colsum_accumulate")
+    return T
+
+
+def mse_accumulate(a: torch.Tensor, b: torch.Tensor, acc: torch.Tensor):
+    """acc (float64[1]) += float mean((a-b)^2)  (awq.py:343-344)."""
+    require_cuda(a, "a")
+    assert a.dtype == b.dtype and a.numel() == b.numel() and acc.dtype == torch.float64
+    a = a.contiguous()
+    b = b.contiguous()
+    check(_lib.load().b200woq_mse_accumulate(ptr(a), ptr(b), dt(a), a.numel(), ptr(acc), stream_ptr(a.device)),
+          "mse_accumulate")
+
+
+def minmax_cols_accumulate(X: torch.Tensor, mx: torch.Tensor, mn: torch.Tensor):
+    require_cuda(X, "X")
+    X2 = X.reshape(-1, X.shape[-1])
+    if not X2.is_contiguous():
+        X2 = X2.contiguous()
+    T, K = X2.shape
+    check(_lib.load().b200woq_minmax_cols_accumulate(ptr(X2), dt(X2), T, K, K, ptr(mx), ptr(mn), stream_ptr(X.device)),
+          "minmax_cols_accumulate")
