@@ -1,0 +1,165 @@
+"""Packed weight-only modules.
+
+Reference: neural_compressor/torch/algorithms/weight_only/modules.py
+    WeightOnlyLinear (ABC)     :91-154
+    INCWeightOnlyLinear        :157-627   (optimum format buffers :236-262, pack :321-375, unpack :377-411,
+                                           recover :413-443, forward :594-610)
+    MulLinear                  :907-949
+
+`B200WeightOnlyLinear` keeps the reference's buffer names, dtypes and shapes (`qweight`, `qzeros`, `scales`,
+`bias`, `g_idx`, `scale_bf16_to_fp8`) so the reference's save/load (`WOQModelLoader`) and HF-format export
+consume it unchanged; pack / unpack / recover / forward are sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import math
+from abc import abstractmethod
+
+import torch
+
+from .. import ops
+
+
+class WeightOnlyLinear(torch.nn.Module):
+    """modules.py:91-154."""
+
+    def __init__(self, in_features, out_features, dtype, bits, group_size, device, scale_dtype=torch.float32, **kwargs):
+        super().__init__()
+        self.dtype = dtype
+        self.bits = bits
+        self.group_size = group_size if group_size != -1 else in_features
+        self.in_features = in_features
+        self.out_features = out_features
+        self.device = device
+        self.scale_dtype = scale_dtype
+
+    @abstractmethod
+    def pack(self, *args, **kwargs):
+        raise NotImplementedError
+
+    @abstractmethod
+    def unpack(self, *args, **kwargs):
+        raise NotImplementedError
+
+    def extra_repr(self) -> str:
+        return "in_features={}, out_features={}, bits={}, group_size={}, bias={}".format(
+            self.in_features, self.out_features, self.bits, self.group_size, self.bias is not None)
+
+
+class B200WeightOnlyLinear(WeightOnlyLinear):
+    """Drop-in for `INCWeightOnlyLinear(use_optimum_format=True)` with the kernels on the B200."""
+
+    def __init__(self, in_features, out_features, dtype="int", bits=4, group_size=32, zp=False, bias=False,
+                 scale_dtype=torch.float32, compression_dtype=torch.int32, compression_dim=1, g_idx=False,
+                 device="cuda", use_optimum_format=True, **kwargs):
+        super().__init__(in_features, out_features, dtype, bits, group_size, device, scale_dtype=scale_dtype)
+        if "int" not in str(dtype):
+            raise NotImplementedError("nf4/fp4 tables are not on the B200 hot path (SURVEY §8 f3)")
+        if not use_optimum_format or compression_dtype != torch.int32:
+            raise NotImplementedError("only the default optimum format (int32, K-major) has B200 kernels")
+        self.use_optimum_format = True
+        self.compression_dtype = torch.int32
+        self.float_type = torch.float16
+        self.compress_bits = 32
+        self.n_pack = 32 // bits
+        ng = math.ceil(in_features / self.group_size)
+        dev = device
+        self.register_buffer("scale_bf16_to_fp8", torch.zeros(1, dtype=torch.bfloat16, device=dev))
+        self.register_buffer("scales", torch.zeros((ng, out_features), dtype=torch.float16, device=dev))
+        self.register_buffer("qweight", torch.zeros((math.ceil(in_features / self.n_pack), out_features),
+                                                    dtype=torch.int32, device=dev))
+        self.register_buffer("qzeros", torch.zeros((ng, math.ceil(out_features / self.n_pack)),
+                                                   dtype=torch.int32, device=dev))
+        self.register_buffer("bias", torch.zeros(out_features, dtype=torch.float16, device=dev))
+        if g_idx:
+            self.register_buffer("g_idx", torch.zeros(in_features, dtype=torch.int32, device=dev))
+        else:
+            self.g_idx = None
+
+    # ------------------------------------------------------------------ pack
+    def pack(self, int_weight, scales, zp, bias, scale_bf16_to_fp8=None, g_idx=None, **kwargs):
+        """modules.py:321-375.  int_weight [N,K] integer-valued (sym: in [-2^(b-1), 2^(b-1)-1], zp None);
+        scales [N,G]; zp [N,G] or None."""
+        dev = self.qweight.device
+        ng = self.scales.shape[0]
+        assert tuple(scales.shape) == (self.out_features, ng), \
+            f"{tuple(scales.shape)} != {(self.out_features, ng)} Scale shape is mismatched."
+        codes = int_weight.to(dev).to(torch.int32)
+        if zp is None:
+            codes = codes + 2 ** (self.bits - 1)
+        codes = (codes & (2**self.bits - 1)).to(torch.uint8).contiguous()
+        self.pack_stored(codes, scales.to(dev), None if zp is None else zp.to(dev), bias, g_idx)
+
+    def pack_stored(self, stored_codes, scales, zp, bias, g_idx=None):
+        """Pack codes that already are the unsigned stored fields (uint8 [N,K])."""
+        self.qweight = ops.pack_codes(stored_codes, self.bits)
+        self.scales, self.qzeros = ops.pack_params(scales, zp, self.bits)
+        self._set_bias_gidx(bias, g_idx)
+
+    def set_packed(self, qweight, qzeros, scales16, bias, g_idx=None):
+        self.qweight, self.qzeros, self.scales = qweight, qzeros, scales16
+        self._set_bias_gidx(bias, g_idx)
+
+    def _set_bias_gidx(self, bias, g_idx):
+        dev = self.qweight.device
+        if bias is not None:
+            self.bias = bias.detach().to(dev).to(self.float_type)
+        if g_idx is not None:
+            assert hasattr(self, "g_idx"), "g_idx is not set when initializing."
+            perm = g_idx.to(dev).to(torch.int64)
+            # optimum format stores the group of each input channel (modules.py:338-344)
+            self.g_idx = (torch.argsort(perm) // self.group_size).to(torch.int32)
+
+    # ------------------------------------------------------------------ unpack / recover / forward
+    def unpack(self):
+        """modules.py:377-411 -> dict(int_weight, scales [N,G], zp, g_idx, bias)."""
+        ng = self.scales.shape[0]
+        codes, zps = ops.unpack(self.qweight, self.qzeros, self.bits, self.in_features, self.out_features, ng)
+        return dict(int_weight=codes.to(torch.int16), scales=self.scales.t().contiguous(),
+                    scale_bf16_to_fp8=self.scale_bf16_to_fp8, zp=zps.to(torch.int16), g_idx=self.g_idx, bias=self.bias)
+
+    def recover(self):
+        """modules.py:413-443: fp16 [N,K] = fp16(int8(q - zp) * scale)."""
+        return ops.dequantize(self.qweight, self.qzeros, self.scales, self.bits, self.group_size, self.in_features,
+                              self.out_features, self.g_idx)
+
+    def forward(self, input, input_scale=None):
+        out_dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16) else torch.float32
+        return ops.woq_linear(input, self.qweight, self.qzeros, self.scales, self.bias, self.bits, self.group_size,
+                              self.in_features, self.out_features, g_idx=self.g_idx, input_scale=input_scale,
+                              out_dtype=out_dtype)
+
+
+class MulLinear(torch.nn.Module):
+    """modules.py:907-949: linear(x * input_scale).  When the wrapped module is packed, the multiply is fused
+    into the dequant-GEMM's activation staging."""
+
+    def __init__(self, module, input_scale=None):
+        super().__init__()
+        if input_scale is None:
+            input_scale = torch.empty(module.in_features)
+        self.register_buffer("input_scale", input_scale)
+        self.add_module("linear", module)
+
+    @property
+    def weight(self):
+        return self.linear.weight
+
+    @weight.setter
+    def weight(self, weight):
+        self.linear.weight = weight
+
+    def forward(self, X):
+        if isinstance(self.linear, B200WeightOnlyLinear):
+            return self.linear(X, input_scale=self.input_scale.float())
+        return self.linear(torch.mul(X, self.input_scale))
+
+    def _update_linear(self):
+        scale = self.input_scale.view(1, self.input_scale.shape[0])
+        with torch.no_grad():
+            self.linear.weight /= scale
+
+    def _recover_linear(self):
+        scale = self.input_scale.view(1, self.input_scale.shape[0])
+        with torch.no_grad():
+            self.linear.weight *= scale

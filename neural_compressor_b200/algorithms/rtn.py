@@ -1,0 +1,111 @@
+"""RTN quantizer.  Reference: neural_compressor/torch/algorithms/weight_only/rtn.py:45-270
+(RTNQuantizer.convert) and utility.py:439-480 (search_clip).
+
+Host Python walks the modules exactly like the reference; the per-layer work -- group min/max, scale and
+zero-point, rounding, bit packing -- is the K4 kernels.  The weights are quantised where the kernels live:
+each Linear's weight is moved to the B200, packed there, and the packed module is placed on the model's
+device (`m.to(device)` / `new_module.to(model_device)`, rtn.py:164-165, 262-264).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..utils import current_device, get_model_device, logger, set_module
+from .base_algorithm import Quantizer
+from .modules import B200WeightOnlyLinear
+
+
+def _supported_layers():
+    types = [torch.nn.Linear]
+    try:
+        import transformers
+
+        types.append(transformers.Conv1D)
+    except Exception:  # pragma: no cover
+        pass
+    return tuple(types)
+
+
+def search_clip(weight: torch.Tensor, bits=4, group_size=32, scheme="asym", enable_full_range=False) -> float:
+    """utility.py:439-480: 40 ratios 1 - i/200, loss = mean((W - qdq(W))^2) over the whole tensor."""
+    best_err, best = float("inf"), None
+    tmp = torch.empty_like(weight)
+    for i in range(int(0.2 * 200)):
+        ratio = 1 - i / 200
+        ops.rtn_fake_quant(weight, bits, group_size, scheme == "sym", enable_full_range, ratio, out=tmp)
+        loss = (weight - tmp).float().pow(2).mean()
+        if loss < best_err:
+            best_err, best = loss, ratio
+    return best
+
+
+class RTNQuantizer(Quantizer):
+    def __init__(self, quant_config=None):
+        super().__init__(quant_config if quant_config is not None else {})
+
+    def prepare(self, model, *args, **kwargs):
+        """rtn.py:57-65: RTN needs no calibration."""
+        return model
+
+    @torch.no_grad()
+    def convert(self, model, dtype="int", bits=4, scheme="sym", group_size=32, group_dim=1, quantile=1.0,
+                use_full_range=False, use_mse_search=False, use_layer_wise=False, model_path="", quant_lm_head=False,
+                *args, **kwargs):
+        weight_config = self.quant_config
+        device = current_device()
+        model_device = get_model_device(model)
+        assert isinstance(model, torch.nn.Module), "only support torch module"
+        if use_layer_wise:
+            logger.info("use_layer_wise is a CPU-RAM saving mode of the reference; weights are streamed to the "
+                        "B200 layer by layer anyway, so it is ignored here.")
+        supported = _supported_layers()
+        try:
+            import transformers
+
+            conv1d = transformers.Conv1D
+        except Exception:  # pragma: no cover
+            conv1d = ()
+        for name, m in list(model.named_modules()):
+            if not isinstance(m, supported) or name not in weight_config:
+                continue
+            cfg = weight_config[name]
+            dtype = cfg.get("dtype", "int")
+            if dtype == "fp32":
+                continue
+            if dtype in ("fp8_e5m2", "fp8_e5m2fnuz", "fp8_e4m3fn", "fp8_e4m3fnuz", "nf4", "fp4", "fp4_e2m1", "fp4_e2m1_bnb"):
+                raise NotImplementedError(f"dtype {dtype} is outside the B200 hot path (SURVEY §8 f3)")
+            bits = cfg.get("bits", 4)
+            if dtype != "int" and "int" in dtype:
+                bits = int(dtype.lstrip("int"))
+                dtype = "int"
+            group_size = cfg["group_size"]
+            scheme = cfg["scheme"]
+            quantile = cfg.get("quantile", 1.0)
+            group_dim = cfg.get("group_dim", 1)
+            use_full_range = cfg.get("use_full_range", False)
+            use_mse_search = cfg.get("use_mse_search", False)
+            if cfg.get("use_double_quant", False):
+                raise NotImplementedError("double quant of scales is outside the B200 hot path (SURVEY §8 f3)")
+            is_conv1d = bool(conv1d) and isinstance(m, conv1d)
+            transpose = (group_dim == 0) ^ is_conv1d   # rtn.py:209-216
+            if group_dim == 0 and not is_conv1d:
+                raise NotImplementedError("group_dim=0 on nn.Linear has no packed B200 layout")
+            w = m.weight.detach().to(device)
+            w = w.t().contiguous() if transpose else w.contiguous()   # [N = out, K = in]
+            if use_mse_search:
+                quantile = search_clip(w, bits, group_size, scheme, use_full_range)
+            r = ops.rtn_quant_pack(w, bits, group_size, scheme == "sym", use_full_range, quantile)
+            if is_conv1d:
+                in_features, out_features = m.weight.shape[0], m.weight.shape[1]
+            else:
+                in_features, out_features = m.in_features, m.out_features
+            new_module = B200WeightOnlyLinear(in_features, out_features, dtype=dtype, bits=bits, group_size=group_size,
+                                              zp=scheme != "sym", bias=m.bias is not None, device=device)
+            new_module.set_packed(r["qweight"], r["qzeros"], r["scales"], m.bias)
+            if model_device.type == "cuda":
+                new_module.to(model_device)
+            if name == "":
+                return new_module
+            set_module(model, name, new_module)
+        return model
