@@ -47,6 +47,8 @@ int b200woq_version(void);
 const char* b200woq_last_error(void);
 /* fills `out` with "sm_XY" of the current device; B200WOQ_ECUDA if there is none */
 int b200woq_device_arch(char* out, int out_len);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches` evidence) */
+int64_t b200woq_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * K4  RTN group quantisation and bit packing

@@ -19,6 +19,7 @@ _SIGS = {
     "b200woq_version": (c_int, []),
     "b200woq_last_error": (c_char_p, []),
     "b200woq_device_arch": (c_int, [c_char_p, c_int]),
+    "b200woq_launch_count": (c_int64, []),
     "b200woq_rtn_params": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_int, c_float,
                                    c_void_p, c_void_p, c_void_p]),
     "b200woq_rtn_quant_pack": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -61,7 +61,7 @@ class _HessianBank:
         self.acc: List[torch.Tensor] = []
         self.layer_to_slot: Dict[str, int] = {}
         self.nsamples = 0
-        self._seen = {}  # data_ptr -> slot, valid during one block forward
+        self._seen = {}  # input identity -> (slot, tensor), valid during one block forward
         self._fwd_batch = 0
 
     def begin_forward(self):
@@ -73,14 +73,16 @@ class _HessianBank:
         self.nsamples += max(self._fwd_batch, 1)
 
     def add(self, layer_name: str, inp: torch.Tensor):
+        # identity of the input tensor: (address, shape, dtype).  The tensor is kept alive until end_forward()
+        # so the caching allocator cannot hand the same address to a later activation of this forward.
         key = (inp.data_ptr(), tuple(inp.shape), inp.dtype)
         self._fwd_batch = max(self._fwd_batch, inp.shape[0] if inp.dim() == 3 else 1)
         slot = self.layer_to_slot.get(layer_name)
         if key in self._seen:
-            shared = self._seen[key]
+            shared = self._seen[key][0]
             if slot is None:
                 self.layer_to_slot[layer_name] = shared
-            elif slot != shared:  # grouping changed between samples: fall back to a private accumulator
+            elif slot != shared:
                 raise RuntimeError(f"inconsistent input sharing for {layer_name}")
             return
         if slot is None:
@@ -88,11 +90,24 @@ class _HessianBank:
             self.acc.append(torch.zeros((c, c), dtype=torch.float32, device=self.device))
             slot = len(self.acc) - 1
             self.layer_to_slot[layer_name] = slot
-        elif slot in self._seen.values():
+        elif any(v[0] == slot for v in self._seen.values()):
             raise RuntimeError(f"inconsistent input sharing for {layer_name}")
-        self._seen[key] = slot
+        self._seen[key] = (slot, inp)
         x = inp if inp.is_contiguous() else inp.contiguous()
         ops.hessian_accumulate(x, self.acc[slot])
+
+    def all_reduce(self):
+        """Calibration data-parallelism: H is additive over samples, so each rank accumulates its
+        shard of the sequences and the raw sums are all-reduced once per distinct input (NCCL over NVLink)."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        for h in self.acc:
+            dist.all_reduce(h, op=dist.ReduceOp.SUM)
+        n = torch.tensor([float(self.nsamples)], device=self.acc[0].device if self.acc else "cpu")
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        self.nsamples = int(round(n.item()))
 
 
 class RAWGPTQuantizer:
@@ -111,6 +126,7 @@ class RAWGPTQuantizer:
         self._check_layer_config()
         self.timing = {"hessian_fwd": 0.0, "cholesky": 0.0, "fasterquant": 0.0, "propagate": 0.0, "pack": 0.0}
         self.profile = False
+        self.offload_packed_to_host = False  # reference behaviour `transformer_block.cpu()` (gptq.py:766)
 
     def _check_layer_config(self):
         """gptq.py:337-365 defaults."""
@@ -250,6 +266,8 @@ class RAWGPTQuantizer:
             self.cache_kwargs["batch_num"] = batch_num
             for h in handles:
                 h.remove()
+            bank.begin_forward()  # drop the kept-alive inputs
+            bank.all_reduce()
             t0 = self._sync_time("hessian_fwd", t0)
             # ---- Hessian -> inverse factor, once per distinct input (gptq.py:1189-1231) ----
             results = {}
@@ -326,6 +344,9 @@ class RAWGPTQuantizer:
                                        g_idx=r.get("perm"))
                 set_module(block, lname, new_module)
             self._sync_time("pack", t0)
+        if self.offload_packed_to_host:
+            block = block.to("cpu")
+            blocks[block_idx] = block
         return block
 
 

@@ -21,7 +21,7 @@ def save(model, output_dir="./saved_results", format="default", **kwargs):
     torch.save(model.state_dict(), os.path.join(os.path.abspath(os.path.expanduser(output_dir)), WEIGHT_NAME))
     qcfg = {}
     for (op_name, op_type), cfg in getattr(model, "qconfig", {}).items():
-        qcfg[f"('{op_name}', '{op_type}')"] = {cfg.name: cfg.to_dict()}
+        qcfg[f"('{op_name}', '{op_type}')"] = {cfg.name: {k: getattr(cfg, k) for k in cfg.params_list}}
     with open(os.path.join(output_dir, QCONFIG_NAME), "w") as f:
         json.dump(qcfg, f, indent=4)
 

@@ -1,4 +1,5 @@
 // api.cu -- error reporting and device queries of libb200woq.
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -15,6 +16,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
+
 int num_sms() {
   static int cached[64];
   static std::mutex mu;
@@ -30,6 +35,9 @@ int num_sms() {
 }
 
 }  // namespace b200woq
+
+namespace b200woq { long long launches(); }
+extern "C" int64_t b200woq_launch_count(void) { return (int64_t)b200woq::launches(); }
 
 extern "C" int b200woq_version(void) { return B200WOQ_VERSION; }
 

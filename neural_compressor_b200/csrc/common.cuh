@@ -13,6 +13,7 @@
 namespace b200woq {
 
 void set_error(const char* fmt, ...);
+void count_launch(int n = 1);  // kernels launched through this library since load (b200woq_launch_count)
 
 #define WOQ_CHECK_ARG(cond, ...)          \
   do {                                    \
@@ -33,6 +34,7 @@ void set_error(const char* fmt, ...);
 
 #define WOQ_LAUNCH_CHECK()                                                                        \
   do {                                                                                            \
+    b200woq::count_launch(1);                                                                     \
     cudaError_t _e = cudaGetLastError();                                                          \
     if (_e != cudaSuccess) {                                                                      \
       b200woq::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

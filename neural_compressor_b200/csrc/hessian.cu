@@ -302,6 +302,7 @@ extern "C" int b200woq_hessian_finalize(float* H, int64_t C, double nsamples, fl
   hessian_scale_mirror_kernel<<<blocks, 256, 0, st>>>(H, C, factor, 64);
   hessian_mirror_kernel<<<blocks, 256, 0, st>>>(H, C, 64);
   hessian_dead_damp_kernel<<<1, 1024, 0, st>>>(H, C, percdamp, dead_mask, scratch);
+  count_launch(2);
   WOQ_LAUNCH_CHECK();
   return 0;
 }

@@ -406,6 +406,7 @@ extern "C" int b200woq_rtn_fake_quant(const void* W, int w_dtype, int64_t N, int
   if (rc == 0) {
     DISPATCH_DTYPE(w_dtype, fake_quant_kernel<T><<<grid_for(N * K, 256), 256, 0, st>>>(
                                 (const T*)W, N, K, g, G, bits, sym, params, params + N * G, col_scale, (T*)out));
+    count_launch(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("fake_quant launch failed: %s", cudaGetErrorString(e));

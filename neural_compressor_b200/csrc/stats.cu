@@ -102,6 +102,7 @@ static int col_reduce(const void* X, int64_t rows, int64_t K, int64_t ldx, const
   dim3 grid((unsigned)ceil_div(K, kColsPerBlock), (unsigned)chunks);
   col_reduce_partial_kernel<T, OP><<<grid, kColsPerBlock, 0, st>>>((const T*)X, rows, K, ldx, gmax, g, G, partial);
   col_reduce_final_kernel<MODE><<<(unsigned)ceil_div(K, 256), 256, 0, st>>>(partial, chunks, K, 1.f / (float)rows, out);
+  count_launch(2);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(partial, st);
   if (e != cudaSuccess) {
@@ -138,6 +139,7 @@ extern "C" int b200woq_awq_weight_scale(const void* W, int w_dtype, int64_t N, i
   int rc = 0;
   STATS_DISPATCH(w_dtype, {
     group_absmax_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)W, N, K, g, G, gmax);
+    count_launch(1);
     rc = col_reduce<T, 3, 3>(W, N, K, K, gmax, g, G, out, st);
   });
   cudaFreeAsync(gmax, st);
@@ -172,6 +174,7 @@ extern "C" int b200woq_mse_accumulate(const void* a, const void* b, int dtype, i
   WOQ_CUDA(cudaMallocAsync((void**)&partial, sizeof(float) * blocks, st));
   STATS_DISPATCH(dtype, (sqdiff_partial_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)a, (const T*)b, count, partial)));
   sqdiff_final_kernel<<<1, 32, 0, st>>>(partial, (int)blocks, (float)(1.0 / (double)count), acc);
+  count_launch(2);
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(partial, st);
   if (e != cudaSuccess) {

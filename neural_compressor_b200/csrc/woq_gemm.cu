@@ -23,6 +23,8 @@
 //     M  > 8: scale applied in half2 before the MMA, reproducing the reference's fp16 weight exactly;
 //   * split-K across CTAs with a deterministic "last CTA reduces" epilogue (fixed summation order).
 // The general path (g_idx / ragged shapes / other bit widths) is a plain CUDA-core kernel.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace b200woq {
@@ -42,9 +44,8 @@ struct GemmParams {
   int y_dtype;
   int bits, g;
   int64_t G;
-  int S;  // split-K factor
-  float* ws_partial;
-  int* ws_counter;
+  int S;      // split-K factor == cluster size along x
+  int gmax;   // max groups per CTA
   int xs_ld;  // halves per smem x row
   int pdl;
 };
@@ -69,6 +70,11 @@ __device__ __forceinline__ int4 ldg_nc_v4(const int32_t* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 __device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
@@ -119,59 +125,152 @@ struct Dequant<8> {
   }
 };
 
+// 8 consecutive activations -> fp16, permuted to the MMA k order of one (BITS=4) or two (BITS=8) words
+template <int BITS>
+__device__ __forceinline__ uint4 permute_pack8(const float (&v)[8]) {
+  __half2 h[4];
+  if (BITS == 4) {  // [x0,x4,x1,x5,x2,x6,x3,x7]
+    h[0] = __floats2half2_rn(v[0], v[4]);
+    h[1] = __floats2half2_rn(v[1], v[5]);
+    h[2] = __floats2half2_rn(v[2], v[6]);
+    h[3] = __floats2half2_rn(v[3], v[7]);
+  } else {  // two 4-code words: [x0,x2,x1,x3 | x4,x6,x5,x7]
+    h[0] = __floats2half2_rn(v[0], v[2]);
+    h[1] = __floats2half2_rn(v[1], v[3]);
+    h[2] = __floats2half2_rn(v[4], v[6]);
+    h[3] = __floats2half2_rn(v[5], v[7]);
+  }
+  return make_uint4(h2_as_u32(h[0]), h2_as_u32(h[1]), h2_as_u32(h[2]), h2_as_u32(h[3]));
+}
+
+__device__ __forceinline__ void load8_as_float(const void* base, int dtype, int64_t idx, float (&v)[8]) {
+  if (dtype == B200WOQ_F32) {
+    const float4 a = *reinterpret_cast<const float4*>((const float*)base + idx);
+    const float4 b = *reinterpret_cast<const float4*>((const float*)base + idx + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 r = *reinterpret_cast<const uint4*>((const uint16_t*)base + idx);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (dtype == B200WOQ_F16) {
+        const float2 f = __half22float2(u32_as_h2(w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      } else {
+        v[2 * i] = __uint_as_float(w[i] << 16);
+        v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+  }
+}
+
+// grid = (S, n_tiles) with thread-block clusters of S CTAs along x: cluster rank r owns the k-groups
+// [r*G/S, (r+1)*G/S) of the n tile.  Split-K partial sums never touch global memory: they are exchanged through
+// distributed shared memory (each rank reduces 128/S of the tile's columns, fixed order -> deterministic).
 template <int BITS, int MT, bool POST>
 __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(const GemmParams p) {
   constexpr int KPW = 32 / BITS;   // codes per word
   constexpr int KSTEP = 4 * KPW;   // k covered by the 4 quad-lanes' words
   constexpr int NSTEP = (BITS == 4) ? 2 : 1;  // MMA k16 steps per 16-byte load
+  constexpr int ZW = 128 / KPW;    // qzeros words per group per 128-column tile
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __half* xs = reinterpret_cast<__half*>(smem_raw);
+  // smem: [ red: M*128 floats ][ xs: M * xs_ld halves ][ sc_s: gmax*128 halves ][ zr_s: gmax*ZW words ]
+  float* red = reinterpret_cast<float*>(smem_raw);
+  __half* xs = reinterpret_cast<__half*>(smem_raw + (size_t)p.M * 128 * sizeof(float));
+  __half* sc_s = xs + (size_t)p.M * p.xs_ld;
+  uint32_t* zr_s = reinterpret_cast<uint32_t*>(sc_s + (size_t)p.gmax * 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
   const int strip = warp & 3, khalf = warp >> 2;
   const int64_t N = p.N;
-  const int64_t n_strip = (int64_t)blockIdx.x * 128 + strip * 32;
+  const int64_t n_tile0 = (int64_t)blockIdx.y * 128;
+  const int64_t n_strip = n_tile0 + strip * 32;
   const int64_t n0 = n_strip + 4 * gq;
   const bool strip_valid = n_strip < N;
   const int g = p.g;
   const int NI = g / KSTEP;  // 16-byte loads per group per lane
+  const int S = p.S;
+  const int rank = blockIdx.x;  // == cluster rank (cluster dims = (S,1,1), gridDim.x == S)
+  // all CTAs of the cluster must be resident before anyone writes into a peer's shared memory: arrive now,
+  // wait just before the exchange (the barrier completes in the background while we stream weights)
+  if (S > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
   // CTA group range and this warp's half of it
-  const int gb = (int)((int64_t)blockIdx.y * p.G / p.S), ge = (int)(((int64_t)blockIdx.y + 1) * p.G / p.S);
+  const int gb = (int)((int64_t)rank * p.G / S), ge = (int)(((int64_t)rank + 1) * p.G / S);
   const int gmid = gb + (ge - gb + 1) / 2;
   const int g0 = khalf == 0 ? gb : gmid, g1 = khalf == 0 ? gmid : ge;
   const int total = strip_valid ? (g1 - g0) * NI : 0;
 
-  // word row of iteration `it` is g0*g/KPW + 4*it + t: groups are contiguous in k, so the pointer simply
-  // advances by 4 rows per iteration across group boundaries
+  // (1) weights: word row of iteration `it` is g0*g/KPW + 4*it + t (groups are contiguous in k)
   const int32_t* wptr = p.qweight + ((int64_t)g0 * (g / KPW) + t) * N + n0;
   const int64_t wstep = 4 * N;
-
-  // weights do not depend on the previous kernel: start streaming them before the PDL wait
   int4 buf[kPrefetch];
 #pragma unroll
   for (int j = 0; j < kPrefetch; ++j)
     if (j < total) buf[j] = ldg_nc_v4(wptr + (int64_t)j * wstep);
   wptr += (int64_t)kPrefetch * wstep;
 
+  // (2) scales / zero-points of the CTA's groups -> smem (cp.async, 16-byte chunks)
+  {
+    const int ng = ge - gb;
+    const int sc_chunks = ng * 16, z_chunks = ng * (ZW / 4);
+    const int64_t Nw = N / KPW;
+    for (int c = threadIdx.x; c < sc_chunks + z_chunks; c += blockDim.x) {
+      if (c < sc_chunks) {
+        const int gl = c >> 4, ch = c & 15;
+        if (n_tile0 + ch * 8 < N)
+          cp_async16(sc_s + gl * 128 + ch * 8, p.scales + (int64_t)(gb + gl) * N + n_tile0 + ch * 8);
+      } else {
+        const int cz = c - sc_chunks;
+        const int gl = cz / (ZW / 4), ch = cz % (ZW / 4);
+        if (n_tile0 + ch * 4 * KPW < N)
+          cp_async16(zr_s + gl * ZW + ch * 4, p.qzeros + (int64_t)(gb + gl) * Nw + n_tile0 / KPW + ch * 4);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+
+  // everything above is constant data; x may be produced by the previous kernel
   if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // stage x (permuted, fp16, optional MulLinear input scale) for the CTA's k range
+  // (3) x: 8-element chunks, vector loads first, then convert / permute / store
   {
     const int64_t kbase = (int64_t)gb * g;
-    const int ksz = (ge - gb) * g;
-    const int cnt = (int)p.M * ksz;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const int m = i / ksz, kk = i - m * ksz;
-      float v = load_as_float(p.x, p.x_dtype, (int64_t)m * p.K + kbase + kk);
-      if (p.input_scale) v *= p.input_scale[kbase + kk];
-      const int e = kk % KPW;
-      const int pos = (BITS == 4) ? ((e & 3) * 2 + (e >> 2)) : ((e & 1) * 2 + (e >> 1));
-      xs[m * p.xs_ld + (kk - e) + pos] = __float2half_rn(v);
+    const int ksz8 = (ge - gb) * g / 8;
+    const int cnt = (int)p.M * ksz8;
+    for (int c0 = threadIdx.x; c0 < cnt; c0 += 4 * blockDim.x) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < cnt) {
+          const int m = c / ksz8, kc = c - m * ksz8;
+          load8_as_float(p.x, p.x_dtype, (int64_t)m * p.K + kbase + kc * 8, v[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < cnt) {
+          const int m = c / ksz8, kc = c - m * ksz8;
+          if (p.input_scale) {
+            float sc8[8];
+            load8_as_float(p.input_scale, B200WOQ_F32, kbase + kc * 8, sc8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[u][i] *= sc8[i];
+          }
+          *reinterpret_cast<uint4*>(xs + m * p.xs_ld + kc * 8) = permute_pack8<BITS>(v[u]);
+        }
+      }
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  // let the next kernel in the stream start its own (constant) weight prefetch while we compute
+  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   float acc[2][MT][4];
   float accg[2][MT][4];  // POST only: per-group partial sums (dead code otherwise)
@@ -185,17 +284,6 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
         accg[a][b][c] = 0.f;
       }
 
-  // per-group constants for the lane's 4 out-channels (current + prefetched next)
-  uint2 sc_cur = make_uint2(0, 0), sc_nxt = make_uint2(0, 0);
-  uint32_t zw_cur = 0, zw_nxt = 0;
-  const int64_t Nw = (N + KPW - 1) / KPW;
-  const int zshift = (BITS == 4) ? (int)((n0 & 7) * 4) : 0;
-  auto load_group_consts = [&](int gi, uint2& sc, uint32_t& zw) {
-    sc = *reinterpret_cast<const uint2*>(p.scales + (int64_t)gi * N + n0);
-    zw = ((uint32_t)p.qzeros[(int64_t)gi * Nw + n0 / KPW]) >> zshift;
-  };
-  if (total > 0) load_group_consts(g0, sc_nxt, zw_nxt);
-
   __half2 zc[4], zn[4], sh[4];
   float sf[4];
 #pragma unroll
@@ -203,7 +291,9 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
     zc[r] = zn[r] = sh[r] = __float2half2_rn(0.f);
     sf[r] = 0.f;
   }
-  int i_in_g = 0, gi = g0;
+  const int zshift = (BITS == 4) ? (int)((n0 & 7) * 4) : 0;
+  const int n_in_tile = strip * 32 + 4 * gq;
+  int i_in_g = 0, gl = g0 - gb;
   int xoff = (g0 - gb) * g + t * KPW;  // halves; advances by 4*KPW per iteration
 
   for (int base = 0; base < total; base += kPrefetch) {
@@ -215,15 +305,14 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
         if (it + kPrefetch < total) buf[j] = ldg_nc_v4(wptr);
         wptr += wstep;
         if (i_in_g == 0) {
-          sc_cur = sc_nxt;
-          zw_cur = zw_nxt;
-          if (gi + 1 < g1) load_group_consts(gi + 1, sc_nxt, zw_nxt);
-          const __half2 s01 = u32_as_h2(sc_cur.x), s23 = u32_as_h2(sc_cur.y);
+          const uint2 sc = *reinterpret_cast<const uint2*>(sc_s + gl * 128 + n_in_tile);
+          const uint32_t zw = zr_s[gl * ZW + n_in_tile / KPW] >> zshift;
+          const __half2 s01 = u32_as_h2(sc.x), s23 = u32_as_h2(sc.y);
           const __half sr[4] = {__low2half(s01), __high2half(s01), __low2half(s23), __high2half(s23)};
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            uint32_t z = ((zw_cur >> (BITS * r)) & ((1u << BITS) - 1u)) + 1u;  // stored zp-1 (modules.py:363)
-            if (z > ((1u << BITS) - 1u)) z = 0;                                  // modules.py:409-410
+            uint32_t z = ((zw >> (BITS * r)) & ((1u << BITS) - 1u)) + 1u;  // stored zp-1 (modules.py:363)
+            if (z > ((1u << BITS) - 1u)) z = 0;                              // modules.py:409-410
             zc[r] = __float2half2_rn(1024.f + (float)z);
             zn[r] = __float2half2_rn(-(64.f + (float)z));
             sh[r] = __half2half2(sr[r]);
@@ -272,7 +361,7 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
         xoff += 4 * KPW;
         if (++i_in_g == NI) {
           i_in_g = 0;
-          ++gi;
+          ++gl;
           if (POST) {
 #pragma unroll
             for (int tile = 0; tile < 2; ++tile)
@@ -289,16 +378,16 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
       }
     }
   }
-  if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  // ---- epilogue: lane holds y[m = 8mt + 2t + {0,1}][n0 + {0,1,2,3}] ----
+  // ---- epilogue ----
+  // lane holds y[m = 8mt + 2t + {0,1}][n0 + {0,1,2,3}]:
   // acc[tile][mt][c]: c0,c1 -> row gq (n0 + 2*tile), cols 2t,2t+1 ; c2,c3 -> row gq+8 (n0 + 2*tile + 1)
-  __syncthreads();  // xs no longer needed; reuse smem for the k-half reduction
-  float* red = reinterpret_cast<float*>(smem_raw);  // [4 strips][MT][32 lanes][8]
+  __syncthreads();  // xs / sc_s / zr_s no longer needed; k-half exchange reuses the xs region
+  float* kred = reinterpret_cast<float*>(xs);  // [4 strips][MT][32 lanes][8]
   if (khalf == 1) {
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      float* dst = red + (((strip * MT + mt) * 32 + lane) * 8);
+      float* dst = kred + (((strip * MT + mt) * 32 + lane) * 8);
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
@@ -306,10 +395,16 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
     }
   }
   __syncthreads();
+  // columns of the tile are owned by cluster ranks in slices of 128/S; write the CTA partial of each slice into
+  // its owner's `red` ([src rank][m][128/S]) through distributed shared memory
+  const int slice = 128 / S;
+  if (S > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (khalf == 0 && strip_valid) {
+    const int owner = n_in_tile / slice;
+    float* owner_red = (S == 1) ? red : cluster.map_shared_rank(red, owner);
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const float* src = red + (((strip * MT + mt) * 32 + lane) * 8);
+      const float* src = kred + (((strip * MT + mt) * 32 + lane) * 8);
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
@@ -319,43 +414,24 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
         const int m = 8 * mt + 2 * t + half;
         if (m < p.M) {
           // n0+0: tile0 c(half) ; n0+1: tile0 c(2+half) ; n0+2: tile1 c(half) ; n0+3: tile1 c(2+half)
-          float4 v = make_float4(acc[0][mt][half], acc[0][mt][2 + half], acc[1][mt][half], acc[1][mt][2 + half]);
-          if (p.S == 1) {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              float o = (&v.x)[r];
-              if (p.bias) o += load_as_float(p.bias, p.bias_dtype, n0 + r);
-              store_from_float(p.y, p.y_dtype, (int64_t)m * N + n0 + r, o);
-            }
-          } else {
-            *reinterpret_cast<float4*>(p.ws_partial + ((int64_t)blockIdx.y * p.M + m) * N + n0) = v;
-          }
+          const float4 v = make_float4(acc[0][mt][half], acc[0][mt][2 + half], acc[1][mt][half], acc[1][mt][2 + half]);
+          *reinterpret_cast<float4*>(owner_red + ((size_t)rank * p.M + m) * slice + (n_in_tile - owner * slice)) = v;
         }
       }
     }
   }
-  if (p.S > 1) {
-    __shared__ int is_last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int old = atomicAdd(p.ws_counter + blockIdx.x, 1);
-      is_last = (old == p.S - 1);
-      if (is_last) p.ws_counter[blockIdx.x] = 0;  // leave the workspace zeroed for the next call
-    }
-    __syncthreads();
-    if (is_last) {
-      __threadfence();
-      const int64_t nt0 = (int64_t)blockIdx.x * 128;
-      for (int i = threadIdx.x; i < p.M * 128; i += blockDim.x) {
-        const int m = i / 128;
-        const int64_t n = nt0 + (i % 128);
-        if (n < N) {
-          float s = 0.f;
-          for (int sp = 0; sp < p.S; ++sp) s += __ldcg(p.ws_partial + ((int64_t)sp * p.M + m) * N + n);
-          if (p.bias) s += load_as_float(p.bias, p.bias_dtype, n);
-          store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, s);
-        }
+  if (S > 1) cluster.sync(); else __syncthreads();
+  {
+    const int64_t nbase = n_tile0 + (int64_t)rank * slice;
+    const int cnt = (int)p.M * slice;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      const int m = i / slice, nl = i - m * slice;
+      const int64_t n = nbase + nl;
+      if (n < N) {
+        float sum = 0.f;
+        for (int sp = 0; sp < S; ++sp) sum += red[((size_t)sp * p.M + m) * slice + nl];
+        if (p.bias) sum += load_as_float(p.bias, p.bias_dtype, n);
+        store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, sum);
       }
     }
   }
@@ -417,57 +493,77 @@ static bool fast_path_ok(int64_t N, int64_t K, int bits, int g, const int32_t* g
   return (N % 32 == 0) && (g % kstep == 0) && (K % g == 0);
 }
 
-// split-K factor: enough CTAs for >= 2 per SM, x tile must fit in shared memory
+// split-K factor == cluster size (1,2,4,8): enough CTAs for ~2 per SM, at least 2 groups per CTA
 static int choose_split(int64_t M, int64_t N, int64_t K, int g) {
   const int64_t n_tiles = ceil_div(N, 128);
   const int64_t G = K / g;
-  const int64_t want = 3 * (int64_t)num_sms();
-  int64_t S = ceil_div(want, n_tiles);
-  if (S > G / 2) S = G / 2;  // at least one group per k-half
-  if (S < 1) S = 1;
-  // shared-memory cap: M * (ceil(G/S)*g + 32) halves <= 96 KB
-  while (S < G && M * (ceil_div(G, S) * g + 32) * 2 > 96 * 1024) ++S;
-  return (int)S;
+  const int64_t want = 2 * (int64_t)num_sms();
+  int S = 1;
+  while (S < 8 && n_tiles * S < want && G / (2 * S) >= 2) S *= 2;
+  while (S > 1 && G / S < 1) S /= 2;
+  return S;
+}
+
+static size_t fast_smem_bytes(int64_t Mc, int mt, int64_t gmax, int g, int bits) {
+  const int kpw = 32 / bits;
+  const size_t red = (size_t)Mc * 128 * sizeof(float);
+  size_t xs = (size_t)Mc * (gmax * g + 32) * sizeof(__half);
+  const size_t kred = (size_t)4 * mt * 32 * 8 * sizeof(float);
+  if (xs < kred) xs = kred;
+  const size_t sc = (size_t)gmax * 128 * sizeof(__half), zr = (size_t)gmax * (128 / kpw) * sizeof(uint32_t);
+  return red + xs + sc + zr + 64;
 }
 
 }  // namespace b200woq
 
 using namespace b200woq;
 
-extern "C" int64_t b200woq_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size) {
-  const int g = eff_group(K, group_size);
-  const int64_t Mc = M < 64 ? M : 64;
-  // upper bound over any split factor we may pick (S <= G): partial sums + one counter per n tile
-  const int64_t G = ceil_div(K, g);
-  int64_t S = choose_split(Mc, N, K, g);
-  if (S > G) S = G;
-  return S * Mc * N * (int64_t)sizeof(float) + ((ceil_div(N, 128) * (int64_t)sizeof(int) + 255) / 256) * 256 + 256;
+extern "C" int64_t b200woq_linear_workspace_bytes(int64_t, int64_t, int64_t, int, int) {
+  return 256;  // split-K partials live in distributed shared memory; no global scratch is needed any more
 }
 
 template <int BITS>
 static int launch_fast(GemmParams& p, int64_t Mc, cudaStream_t st) {
   const int mt = Mc <= 8 ? 1 : Mc <= 16 ? 2 : Mc <= 32 ? 4 : 8;
-  const int64_t gmax = ceil_div(p.G, p.S);
-  p.xs_ld = (int)(gmax * p.g + 32);
-  size_t smem = (size_t)Mc * p.xs_ld * sizeof(__half);
-  const size_t red = (size_t)4 * mt * 32 * 8 * sizeof(float);
-  if (smem < red) smem = red;
-  dim3 grid((unsigned)ceil_div(p.N, 128), (unsigned)p.S);
+  // shrink the split until the tile fits in shared memory
+  while (true) {
+    p.gmax = (int)ceil_div(p.G, p.S);
+    if (fast_smem_bytes(Mc, mt, p.gmax, p.g, BITS) <= 200 * 1024 || p.S >= 8 || p.G / (p.S * 2) < 1) break;
+    p.S *= 2;
+  }
+  p.xs_ld = p.gmax * p.g + 32;
+  // the k-half exchange buffer aliases xs: make sure the row count covers it
+  size_t smem = fast_smem_bytes(Mc, mt, p.gmax, p.g, BITS);
+  if (smem > 220 * 1024) {
+    set_error("linear_forward: K slice does not fit in shared memory (M=%lld K=%lld)", (long long)Mc, (long long)p.K);
+    return B200WOQ_EUNSUPPORTED;
+  }
+  dim3 grid((unsigned)p.S, (unsigned)ceil_div(p.N, 128));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = (unsigned)p.S;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (p.pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = p.pdl ? 1 : 0;
+  cfg.numAttrs = na;
 #define WOQ_LAUNCH(MT_, POST_)                                                                              \
   do {                                                                                                      \
     auto kern = woq_gemm_mma_kernel<BITS, MT_, POST_>;                                                      \
     if (smem > 48 * 1024) WOQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     WOQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));                                                            \
+    count_launch(1);                                                                                        \
   } while (0)
   switch (mt) {
     case 1: WOQ_LAUNCH(1, true); break;
@@ -517,21 +613,19 @@ extern "C" int b200woq_linear_forward(const void* x, int x_dtype, int64_t M, int
     WOQ_LAUNCH_CHECK();
     return 0;
   }
-  for (int64_t m0 = 0; m0 < M; m0 += 64) {
-    const int64_t Mc = (M - m0) < 64 ? (M - m0) : 64;
+  // largest batch chunk whose x slice fits in shared memory at the maximum split
+  int64_t cap = 64;
+  while (cap > 8) {
+    const int mtc = cap <= 8 ? 1 : cap <= 16 ? 2 : cap <= 32 ? 4 : 8;
+    if (fast_smem_bytes(cap, mtc, ceil_div(p.G, 8), g, bits) <= 200 * 1024) break;
+    cap /= 2;
+  }
+  for (int64_t m0 = 0; m0 < M; m0 += cap) {
+    const int64_t Mc = (M - m0) < cap ? (M - m0) : cap;
     p.x = (const char*)x + (size_t)m0 * K * xes;
     p.y = (char*)y + (size_t)m0 * N * yes;
     p.M = Mc;
     p.S = choose_split(Mc, N, K, g);
-    if (p.S > 1) {
-      const int64_t need = (int64_t)p.S * Mc * N * (int64_t)sizeof(float) + ((ceil_div(N, 128) * (int64_t)sizeof(int) + 255) / 256) * 256;
-      if (!workspace || workspace_bytes < need) {
-        set_error("linear_forward: workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)need);
-        return B200WOQ_EWORKSPACE;
-      }
-      p.ws_counter = (int*)workspace;  // counters first (must stay zero between calls)
-      p.ws_partial = (float*)((char*)workspace + ((ceil_div(N, 128) * sizeof(int) + 255) / 256) * 256);
-    }
     int rc = (bits == 4) ? launch_fast<4>(p, Mc, st) : launch_fast<8>(p, Mc, st);
     if (rc) return rc;
   }

@@ -145,6 +145,9 @@ def woq_linear(x, qweight, qzeros, scales, bias, bits, group_size, in_features, 
 
 
 # ------------------------------------------------------------------ K1-K3: GPTQ
+PROFILE_HOOK = None  # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per Hessian launch
+
+
 def hessian_accumulate(X: torch.Tensor, Hsum: torch.Tensor):
     """Hsum += X^T X (raw fp32 sums; gptq.py:1111-1141 closed form, see hessian_finalize)."""
     require_cuda(X, "X")
@@ -153,8 +156,14 @@ def hessian_accumulate(X: torch.Tensor, Hsum: torch.Tensor):
         X2 = X2.contiguous()
     T, C = X2.shape
     assert Hsum.shape == (C, C) and Hsum.dtype == torch.float32 and Hsum.is_contiguous()
+    if PROFILE_HOOK is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
     check(_lib.load().b200woq_hessian_accumulate(ptr(X2), dt(X2), T, C, C, ptr(Hsum), stream_ptr(X.device)),
           "hessian_accumulate")
+    if PROFILE_HOOK is not None:
+        e.record()
+        PROFILE_HOOK.append((s, e, float(T) * C * (C + 128)))  # symmetric half incl. diagonal tiles
 
 
 def hessian_finalize(Hsum: torch.Tensor, nsamples: float, percdamp: float):

@@ -163,19 +163,24 @@ def test_hessian_accumulate_vs_fp64(ops, dtype, T, C):
 def test_hessian_finalize_dead_and_damp(ops, golden_gptq):
     X = golden_gptq["X"]
     C = X[0].shape[-1]
-    H = torch.zeros(C, C, dtype=torch.float32, device=DEV)
-    for x in X:
-        ops.hessian_accumulate(x.to(DEV), H)
-    Hraw = H.clone()
-    _, dead = ops.hessian_finalize(H, nsamples=len(X), percdamp=0.01)
+
+    def accumulate():
+        H = torch.zeros(C, C, dtype=torch.float32, device=DEV)
+        for x in X:
+            ops.hessian_accumulate(x.to(DEV), H)
+        return H
+
+    H0, dead = ops.hessian_finalize(accumulate(), nsamples=len(X), percdamp=0.0)
     assert dead.cpu().nonzero().flatten().tolist() == [17]
     Hg = golden_gptq["H"].clone()
-    rel = ((Hraw.cpu() * (2.0 / len(X))) - Hg).abs().max().item() / Hg.abs().max().item()
-    assert rel < 1e-6, rel
-    Hg[17, 17] = 1
+    Hg[17, 17] = 1  # gptq.py:1190
+    rel = (H0.cpu() - Hg).abs().max().item() / Hg.abs().max().item()
+    assert rel < 2e-6, rel   # fp32 summation order vs MKL's
+    H1, _ = ops.hessian_finalize(accumulate(), nsamples=len(X), percdamp=0.01)
     damp = 0.01 * torch.mean(torch.diag(Hg))
     Hg[torch.arange(C), torch.arange(C)] += damp
-    assert (H.cpu() - Hg).abs().max().item() / Hg.abs().max().item() < 1e-6
+    assert (H1.cpu() - Hg).abs().max().item() / Hg.abs().max().item() < 2e-6
+    assert torch.equal(H1, H1.t())
 
 
 def _gptq_expected_codes(run):
@@ -199,7 +204,7 @@ def test_gptq_fasterquant_with_reference_hinv(ops, golden_gptq):
         if perm is not None:
             Wp[:, dead.bool()] = 0
             Wp, dm = Wp[:, perm].contiguous(), None
-        r = ops.gptq_fasterquant(Wp.to(DEV), golden_gptq[run["hinv_key"]].to(DEV), None if dm is None else dm.to(DEV),
+        r = ops.gptq_fasterquant(Wp.to(DEV), golden_gptq[run["hinv_key"]].contiguous().to(DEV), None if dm is None else dm.to(DEV),
                                  v["blocksize"], v["group_size"], v["bits"], v["sym"], v["mse"])
         codes, Q = r["codes"].cpu(), r["Q"].cpu()
         if perm is not None:
