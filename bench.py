@@ -39,6 +39,14 @@ LINEARS = [("q", HIDDEN, HIDDEN), ("k", HIDDEN, HIDDEN), ("v", HIDDEN, HIDDEN), 
            ("gate", INTER, HIDDEN), ("up", INTER, HIDDEN), ("down", HIDDEN, INTER)]
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -129,7 +137,9 @@ def run_b200(args):
     pk = peaks()
     W, K = args.warmup, args.steps
     n_blocks_needed = min(LAYERS, 2 * (W + K)) if args.e2e else min(LAYERS, W + K)
+    log(f"building Llama-2-7B-shape model with {n_blocks_needed} of {LAYERS} blocks on {dev}")
     model = build_llama(dev, n_blocks_needed)
+    log("model built")
 
     cfg = Q.GPTQConfig(bits=4, group_size=128, use_sym=True, act_order=False, block_size=128, percdamp=0.01)
     model = Q.prepare(model, cfg)
@@ -138,6 +148,7 @@ def run_b200(args):
     with torch.no_grad():
         for ids in calib_ids(dev, lo, hi):
             model(ids)
+    log(f"captured block-0 inputs of {hi - lo} sequences")
     engine = model.quantizer.gptq_quantizer
     engine.remove_prepare_for_calibration()
     engine.world_size, engine.rank = world, rank
@@ -175,12 +186,15 @@ def run_b200(args):
     with torch.no_grad():
         for b in range(W):  # warm-up steps (blocks 0..W-1)
             engine.quantize_block(b)
+            torch.cuda.synchronize()
+            log(f"warm-up block {b} done")
     hess_events.clear()
     sampler = ClockSampler(local)
     sampler.start()
     ms_total, launches = timed_blocks(W, K, host_resident=False)
     clocks = sampler.stop()
     ms_step = ms_total / K
+    log(f"timed {K} blocks: {ms_step:.1f} ms/step")
     value = TOKENS / (ms_step * LAYERS / 1000.0)
 
     # dominant kernel: Hessian SYRK
@@ -202,6 +216,7 @@ def run_b200(args):
     if args.e2e and W + K + K <= n_blocks_needed:
         blk_bytes = sum(p_.numel() * p_.element_size() for p_ in engine.blocks_info["transformers"][W + K].parameters())
         ms_e2e, _ = timed_blocks(W + K, K, host_resident=True)
+        log(f"e2e {K} blocks: {ms_e2e / K:.1f} ms/step")
         d2h = sum(b_.numel() * b_.element_size() for b_ in engine.blocks_info["transformers"][W + K].buffers())
         e2e = dict(value=round(TOKENS / (ms_e2e / K * LAYERS / 1000.0), 1), unit="calib tokens/s",
                    h2d_bytes_per_step=blk_bytes, d2h_bytes_per_step=d2h, ms_per_step=round(ms_e2e / K, 2))
@@ -216,9 +231,13 @@ def run_b200(args):
                            l2="inputs >> L2 (2.1 GB activations, 0.4 GB weights per step)"),
                gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline)
     if rank == 0 and args.decode:
+        del model, engine
+        torch.cuda.empty_cache()
         out.update(bench_decode(dev, pk))
+        log("decode bench done")
     if rank == 0 and world == 1 and args.cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(sample_layers=1)
+        log("cpu baseline done")
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
