@@ -144,7 +144,9 @@ def run_b200(args):
     cfg = Q.GPTQConfig(bits=4, group_size=128, use_sym=True, act_order=False, block_size=128, percdamp=0.01)
     model = Q.prepare(model, cfg)
     # strong scaling: the 128 calibration sequences are split over the ranks (Hessians all-reduced)
-    lo, hi = rank * N_SAMPLES // world, (rank + 1) * N_SAMPLES // world
+    from neural_compressor_b200.algorithms.gptq import shard_range
+
+    lo, hi = shard_range(N_SAMPLES, rank, world)
     with torch.no_grad():
         for ids in calib_ids(dev, lo, hi):
             model(ids)
@@ -316,6 +318,10 @@ def cpu_baseline(sample_layers=1):
         t0 = time.perf_counter()
         lay.add_batch(x)
         t_add[C] = time.perf_counter() - t0
+    # column loop: thousands of tiny torch ops -- it does not scale past ~16 threads (more threads only add
+    # fork/join overhead), so cap it there; add_batch above used every core
+    fq_threads = min(cores, 16)
+    torch.set_num_threads(fq_threads)
     lay = O.GPTQLayerOracle(HIDDEN, HIDDEN, bits=4, sym=True)
     for _ in range(3):
         lay.add_batch(torch.randn(1, SEQ, HIDDEN, generator=g))
@@ -327,10 +333,12 @@ def cpu_baseline(sample_layers=1):
     codes = O.GPTQLayerOracle.export_codes(r["Q"], r["scale"], r["zero"], 128, True)
     O.pack_optimum(codes, r["scale"], None, 4, 128)
     t_pack = time.perf_counter() - t0
+    torch.set_num_threads(cores)
     fq_units = sum(N * Kd * Kd for _, N, Kd in LINEARS) / (HIDDEN**3)
     per_block = N_SAMPLES * (6 * t_add[HIDDEN] + t_add[INTER]) + t_fq * fq_units + t_pack * (sum(N * Kd for _, N, Kd in LINEARS) / HIDDEN**2)
     total = per_block * LAYERS
     return dict(value=round(TOKENS / total, 3), unit="calib tokens/s", cores=cores, kind="port",
+                fasterquant_threads=fq_threads,
                 sample=f"add_batch 1x{SEQ} tokens @C=4096 ({t_add[HIDDEN]:.3f}s) and @C=11008 ({t_add[INTER]:.3f}s), "
                        f"fasterquant+export+pack of one 4096x4096 layer ({t_fq:.2f}s+{t_pack:.2f}s); extrapolated x128 "
                        f"samples x 7 Hessians x 32 blocks, fasterquant scaled by N*C^2, block forwards not counted",

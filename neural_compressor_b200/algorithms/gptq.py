@@ -16,6 +16,7 @@ export).  Everything numeric runs on the B200:
 from __future__ import annotations
 
 import math
+import os
 import time
 from functools import partial
 from typing import Dict, List
@@ -51,6 +52,11 @@ def trace_gptq_target_blocks(model):
     if not found:
         raise ValueError("GPTQ needs a model with an nn.ModuleList of transformer blocks")
     return info
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous shard [lo, hi) of the calibration sequences owned by `rank` (strong scaling over samples)."""
+    return rank * n_items // world, (rank + 1) * n_items // world
 
 
 class _HessianBank:
@@ -199,6 +205,56 @@ class RAWGPTQuantizer:
         self.model.forward = self._model_forward
         self.blocks_info["transformers"][0].forward = self._block0_forward
 
+    @staticmethod
+    def _same(a, b) -> bool:
+        if isinstance(a, torch.Tensor) and isinstance(b, torch.Tensor):
+            return a.shape == b.shape and a.dtype == b.dtype and (a.data_ptr() == b.data_ptr() or torch.equal(a, b))
+        if isinstance(a, (tuple, list)) and isinstance(b, (tuple, list)) and len(a) == len(b):
+            return all(RAWGPTQuantizer._same(x, y) for x, y in zip(a, b))
+        return a is b or a == b
+
+    def rechunk_calibration(self, batch=None):
+        """Process `batch` cached sequences per block forward instead of one (the reference runs them one by one,
+        gptq.py:680-685).  Sequences are independent inside a decoder block, so the Hessians and the propagated
+        outputs are the same up to GEMM rounding; the forward GEMMs and the Hessian launches get 8x larger tiles.
+        Only done when every sequence has the same shape and identical auxiliary inputs (position embeddings, mask);
+        B200WOQ_CALIB_BATCH=1 restores the one-by-one schedule."""
+        if getattr(self, "_chunked", False):
+            return
+        self._chunked = True
+        B = int(os.environ.get("B200WOQ_CALIB_BATCH", "8")) if batch is None else batch
+        n = self.cache_kwargs.get("batch_num", 0)
+        if B <= 1 or n <= 1:
+            return
+        in_kwargs = "hidden_states" in self.cache_kwargs
+        hs = self.cache_kwargs["hidden_states"] if in_kwargs else (self.cache_args[0] if self.cache_args else None)
+        if hs is None or any((h.dim() != 3 or h.shape[0] != 1 or h.shape != hs[0].shape) for h in hs):
+            return
+        for k, v in self.cache_kwargs.items():
+            if k in ("batch_num", "hidden_states"):
+                continue
+            if len(v) != n or not all(self._same(v[0], x) for x in v[1:]):
+                return
+        for idx, lst in enumerate(self.cache_args):
+            if idx == 0 and not in_kwargs:
+                continue
+            if len(lst) != n or not all(self._same(lst[0], x) for x in lst[1:]):
+                return
+        chunks = [torch.cat(hs[i:i + B], dim=0) for i in range(0, n, B)]
+        m = len(chunks)
+        for k in list(self.cache_kwargs):
+            if k not in ("batch_num", "hidden_states"):
+                self.cache_kwargs[k] = [self.cache_kwargs[k][0]] * m
+        for idx in range(len(self.cache_args)):
+            if not (idx == 0 and not in_kwargs):
+                self.cache_args[idx] = [self.cache_args[idx][0]] * m
+        if in_kwargs:
+            self.cache_kwargs["hidden_states"] = chunks
+        else:
+            self.cache_args[0] = chunks
+        self.cache_kwargs["batch_num"] = m
+        logger.info(f"calibration forwards batched: {n} sequences -> {m} chunks of <= {B}")
+
     def _batch(self, j):
         kw = {k: v[j] for k, v in self.cache_kwargs.items()}
         args = [a[j] for a in self.cache_args]
@@ -245,6 +301,7 @@ class RAWGPTQuantizer:
     @torch.no_grad()
     def quantize_block(self, block_idx: int):
         blocks = self.blocks_info["transformers"]
+        self.rechunk_calibration()
         block = blocks[block_idx].to(self.device)
         sub_layers = find_layers(block)
         for sequential in self._sequentials(block):

@@ -11,10 +11,14 @@
 //     only tiles on/above the diagonal (SYRK), 4-stage cp.async pipeline of [32 tokens x 128 ch] slabs,
 //     ldmatrix.trans feeds mma.sync.m16n8k16 directly from the token-major slabs.
 //   * fp32 activations (tiny unit-test models): exact fp32 FFMA tiles (generic kernel below).
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace b200woq {
 
+constexpr bool kHessianDefaultTc = false;  // flipped once the tcgen05 kernel is parity-green on hardware
 constexpr int HT = 128;      // output tile edge
 constexpr int HBK = 32;      // tokens per pipeline stage
 constexpr int HLD = HT + 8;  // padded smem row (halves): 272 B rows -> conflict-free ldmatrix
@@ -245,6 +249,10 @@ __global__ void __launch_bounds__(1024) hessian_dead_damp_kernel(float* __restri
 
 }  // namespace b200woq
 
+namespace b200woq {
+int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C, int64_t ldx, float* Hsum, cudaStream_t st);
+}
+
 using namespace b200woq;
 
 // which tile edge owns the "computed" upper region for a given (dtype, alignment)
@@ -261,6 +269,13 @@ extern "C" int b200woq_hessian_accumulate(const void* X, int x_dtype, int64_t T,
   // the SIMT kernel uses 64-tiles but (i/64 <= j/64) is a superset of the 128-tile upper region only
   // when restricted properly, so it always computes every 64-tile with (i/128 <= j/128).
   const int edge = hessian_tile_edge(x_dtype, C, ldx, X);
+  // B200WOQ_HESSIAN_IMPL = "tc" (tcgen05 + TMA + TMEM, hessian_tc.cu) | "mma" (mma.sync + ldmatrix, below)
+  const char* impl = getenv("B200WOQ_HESSIAN_IMPL");
+  const bool want_tc = impl ? (strcmp(impl, "tc") == 0) : kHessianDefaultTc;
+  if (want_tc && edge == HT) {
+    const int rc = hessian_accumulate_tcgen05(X, x_dtype, T, C, ldx, Hsum, st);
+    if (rc != B200WOQ_EUNSUPPORTED) return rc;
+  }
   if (edge == HT) {
     const unsigned nt = (unsigned)ceil_div(C, HT);
     const size_t smem = (size_t)HSTAGES * 2 * HBK * HLD * 2;

@@ -1,0 +1,253 @@
+// hessian_tc.cu -- K1 on the 5th-generation tensor cores: H += X^T X with tcgen05.mma, TMA and TMEM.
+//
+// X is [T, C] token-major (fp16 or bf16).  H[i,j] = sum_t X[t,i] X[t,j]: the contraction index is the SLOW axis of X,
+// so both MMA operands are "MN-major" (for a fixed token the 64 channels of a box are contiguous).  A TMA box of
+// [BK tokens x 64 channels] with the 128-byte swizzle lands in shared memory exactly as the canonical MN-major
+// SWIZZLE_128B UMMA layout:  ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO))  elements,  LBO = BK*128 B (next 64 channels),
+// SBO = 1024 B (next 8 tokens).  No transposes, no ldmatrix: the slabs stream HBM/L2 -> smem -> tensor core.
+//
+//   tile        128 (i) x 256 (j) fp32 accumulator = 256 TMEM columns, one CTA per tile, tiles with 128-row block
+//               ti <= 2*tj+1 only (SYRK: upper block triangle, the rest is mirrored in b200woq_hessian_finalize)
+//   pipeline    4 stages x (A: 2 boxes, B: 4 boxes) = 48 KB per stage, mbarrier full/empty ring
+//   warp roles  warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer (1 lane), warps 2-5 = epilogue
+//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16, both operands MN-major, fp32 accumulate
+//   epilogue    tcgen05.ld 32x32b.x32 -> registers -> read-modify-write of the fp32 H tile (owned by this CTA)
+//
+// fp16 x fp16 (11-bit mantissas) products are exact in fp32, so one pass is fp32-grade.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace b200woq {
+
+namespace tc {
+
+constexpr int TM = 128, TN = 256, BK = 64, STAGES = 4;
+constexpr int BOX_BYTES = BK * 128;            // [BK tokens][64 ch] 16-bit
+constexpr int A_BYTES = (TM / 64) * BOX_BYTES; // 16 KB
+constexpr int B_BYTES = (TN / 64) * BOX_BYTES; // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// MN-major, SWIZZLE_128B shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  constexpr uint64_t LBO = (uint64_t)(BOX_BYTES >> 4);  // next 64-channel atom
+  constexpr uint64_t SBO = (uint64_t)(1024 >> 4);       // next 8-token group
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (LBO << 16) | (SBO << 32) | (1ull << 46) /*version*/ |
+         (2ull << 61) /*SWIZZLE_128B*/;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// grid = (ceil(C/256), ceil(C/128)); block = 192 threads
+__global__ void __launch_bounds__(192, 1)
+    hessian_syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t Ttok, int64_t C, float* __restrict__ H,
+                           uint32_t idesc) {
+  const int tj = blockIdx.x, ti = blockIdx.y;
+  if (ti > 2 * tj + 1) return;  // below the block diagonal: mirrored later
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t bars = base + STAGES * STAGE_BYTES;            // full[S], empty[S], accum, tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  const uint32_t accum_bar = bars + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)ti * TM, j0 = (int64_t)tj * TN;
+  const int nk = (int)((Ttok + BK - 1) / BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), STAGE_BYTES);
+        const uint32_t sa = base + s * STAGE_BYTES;
+        const int t0 = kb * BK;
+#pragma unroll
+        for (int b = 0; b < TM / 64; ++b) tma_load_2d(sa + b * BOX_BYTES, &tmap, full_bar(s), (int)(i0 + 64 * b), t0);
+#pragma unroll
+        for (int b = 0; b < TN / 64; ++b)
+          tma_load_2d(sa + A_BYTES + b * BOX_BYTES, &tmap, full_bar(s), (int)(j0 + 64 * b), t0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * STAGE_BYTES;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 16; ++k4) {
+          const uint64_t ad = make_desc(sa + k4 * 2048);            // 16 tokens = 2 groups of 8 x 128 B rows
+          const uint64_t bd = make_desc(sa + A_BYTES + k4 * 2048);
+          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(accum_bar);       // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;
+    const int64_t row = i0 + q * 32 + lane;
+#pragma unroll 1
+    for (int cc = 0; cc < TN / 32; ++cc) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), r);
+      const int64_t col0 = j0 + cc * 32;
+      if (row < C && col0 < C) {
+        float* dst = H + row * C + col0;
+        if (col0 + 32 <= C && ((C & 3) == 0)) {
+#pragma unroll
+          for (int v = 0; v < 8; ++v) {
+            float4 h = *reinterpret_cast<float4*>(dst + 4 * v);
+            h.x += __uint_as_float(r[4 * v + 0]);
+            h.y += __uint_as_float(r[4 * v + 1]);
+            h.z += __uint_as_float(r[4 * v + 2]);
+            h.w += __uint_as_float(r[4 * v + 3]);
+            *reinterpret_cast<float4*>(dst + 4 * v) = h;
+          }
+        } else {
+          for (int v = 0; v < 32; ++v)
+            if (col0 + v < C) dst[v] += __uint_as_float(r[v]);
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+}  // namespace tc
+
+// returns 0 on success, B200WOQ_EUNSUPPORTED when the shape/alignment needs the legacy kernel
+int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C, int64_t ldx, float* Hsum, cudaStream_t st) {
+  using namespace tc;
+  if (x_dtype != B200WOQ_F16 && x_dtype != B200WOQ_BF16) return B200WOQ_EUNSUPPORTED;
+  if ((C % 8) || (ldx % 8) || (((uintptr_t)X) & 15) || T >= (1ll << 31) || C >= (1ll << 31)) return B200WOQ_EUNSUPPORTED;
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return B200WOQ_EUNSUPPORTED;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)T};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)BK};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(&tmap, x_dtype == B200WOQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return B200WOQ_ECUDA;
+  }
+  // instruction descriptor (cute/arch/mma_sm100_desc.hpp: InstrDescriptor): D=f32, A/B format, both MN-major, N=256, M=128
+  const uint32_t fmt = (x_dtype == B200WOQ_F16) ? 0u : 1u;
+  const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
+                         ((uint32_t)(TM >> 4) << 24);
+  static bool attr_set = false;
+  if (!attr_set) {
+    WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ceil_div(C, TN), (unsigned)ceil_div(C, TM));
+  hessian_syrk_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, T, C, Hsum, idesc);
+  WOQ_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace b200woq

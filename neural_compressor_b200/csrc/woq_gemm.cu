@@ -165,10 +165,20 @@ __device__ __forceinline__ void load8_as_float(const void* base, int dtype, int6
 }
 
 // grid = (S, n_tiles) with thread-block clusters of S CTAs along x: cluster rank r owns the k-groups
-// [r*G/S, (r+1)*G/S) of the n tile.  Split-K partial sums never touch global memory: they are exchanged through
-// distributed shared memory (each rank reduces 128/S of the tile's columns, fixed order -> deterministic).
-template <int BITS, int MT, bool POST>
+// [r*G/S, (r+1)*G/S) of the n tile.  Split-K partial sums never touch global memory: every warp writes its partial
+// straight into the distributed shared memory of the rank that owns its columns (each rank reduces 128/S columns of
+// the tile over the 2*S sources in a fixed order -> deterministic, no atomics, no global scratch).
+//
+// SUB (4-bit, M <= 16): the codes enter the tensor core as fp16 SUBNORMALS.  `w & 0x000f000f` *is* the half2
+// (q_lo * 2^-24, q_hi * 2^-24) -- no magic-number add, no half2 arithmetic at all: 7 integer ops per 8 codes.
+// Products q*2^-24*x are exact in the fp32 accumulator; per group the zero-point is applied algebraically,
+//     sum_k (q_k - z) x_k = 2^24 * acc_g - z * X_g ,   X_g = sum_{k in group} x_k  (fp32, once per CTA),
+// and the group scale multiplies the result in fp32.  This is the exact (q-z)*scale product, i.e. slightly MORE
+// accurate than the reference's fp16-rounded weight fp16((q-z)*scale); the difference is <= 2^-11 relative per weight.
+// !SUB: codes -> (q - z) via the 0x6400 magic number, times the fp16 scale in half2 = the reference's fp16 weight.
+template <int BITS, int MT, bool SUB>
 __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(const GemmParams p) {
+  static_assert(!SUB || BITS == 4, "subnormal-code path is 4-bit only");
   constexpr int KPW = 32 / BITS;   // codes per word
   constexpr int KSTEP = 4 * KPW;   // k covered by the 4 quad-lanes' words
   constexpr int NSTEP = (BITS == 4) ? 2 : 1;  // MMA k16 steps per 16-byte load
@@ -176,20 +186,21 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  // smem: [ red: M*128 floats ][ xs: M * xs_ld halves ][ sc_s: gmax*128 halves ][ zr_s: gmax*ZW words ]
+  // smem: [ red: 2*M*128 floats ][ xs: M*xs_ld halves ][ xsum: M*gmax floats ][ sc_s: gmax*128 halves ][ zr_s ]
   float* red = reinterpret_cast<float*>(smem_raw);
-  __half* xs = reinterpret_cast<__half*>(smem_raw + (size_t)p.M * 128 * sizeof(float));
-  __half* sc_s = xs + (size_t)p.M * p.xs_ld;
+  __half* xs = reinterpret_cast<__half*>(smem_raw + (size_t)2 * p.M * 128 * sizeof(float));
+  float* xsum = reinterpret_cast<float*>(xs + (size_t)p.M * p.xs_ld);
+  __half* sc_s = reinterpret_cast<__half*>(xsum + (size_t)p.M * p.gmax);
   uint32_t* zr_s = reinterpret_cast<uint32_t*>(sc_s + (size_t)p.gmax * 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
   const int strip = warp & 3, khalf = warp >> 2;
-  const int64_t N = p.N;
-  const int64_t n_tile0 = (int64_t)blockIdx.y * 128;
-  const int64_t n_strip = n_tile0 + strip * 32;
-  const int64_t n0 = n_strip + 4 * gq;
-  const bool strip_valid = n_strip < N;
+  const int N = (int)p.N;
+  const int n_tile0 = blockIdx.y * 128;
+  const int n_in_tile = strip * 32 + 4 * gq;
+  const int n0 = n_tile0 + n_in_tile;
+  const bool strip_valid = n_tile0 + strip * 32 < N;
   const int g = p.g;
   const int NI = g / KSTEP;  // 16-byte loads per group per lane
   const int S = p.S;
@@ -199,14 +210,15 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   if (S > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
   // CTA group range and this warp's half of it
-  const int gb = (int)((int64_t)rank * p.G / S), ge = (int)(((int64_t)rank + 1) * p.G / S);
+  const int Gt = (int)p.G;
+  const int gb = rank * Gt / S, ge = (rank + 1) * Gt / S;
   const int gmid = gb + (ge - gb + 1) / 2;
   const int g0 = khalf == 0 ? gb : gmid, g1 = khalf == 0 ? gmid : ge;
   const int total = strip_valid ? (g1 - g0) * NI : 0;
 
   // (1) weights: word row of iteration `it` is g0*g/KPW + 4*it + t (groups are contiguous in k)
   const int32_t* wptr = p.qweight + ((int64_t)g0 * (g / KPW) + t) * N + n0;
-  const int64_t wstep = 4 * N;
+  const int64_t wstep = 4 * (int64_t)N;
   int4 buf[kPrefetch];
 #pragma unroll
   for (int j = 0; j < kPrefetch; ++j)
@@ -217,8 +229,8 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   {
     const int ng = ge - gb;
     const int sc_chunks = ng * 16, z_chunks = ng * (ZW / 4);
-    const int64_t Nw = N / KPW;
-    for (int c = threadIdx.x; c < sc_chunks + z_chunks; c += blockDim.x) {
+    const int Nw = N / KPW;
+    for (int c = threadIdx.x; c < sc_chunks + z_chunks; c += 256) {
       if (c < sc_chunks) {
         const int gl = c >> 4, ch = c & 15;
         if (n_tile0 + ch * 8 < N)
@@ -236,34 +248,22 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   // everything above is constant data; x may be produced by the previous kernel
   if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // (3) x: 8-element chunks, vector loads first, then convert / permute / store
+  // (3) x: 8-element chunks (m outer, chunk inner: no divisions), vector loads, convert / permute / store
   {
     const int64_t kbase = (int64_t)gb * g;
     const int ksz8 = (ge - gb) * g / 8;
-    const int cnt = (int)p.M * ksz8;
-    for (int c0 = threadIdx.x; c0 < cnt; c0 += 4 * blockDim.x) {
-      float v[4][8];
+    for (int m = 0; m < (int)p.M; ++m) {
+      const int64_t row = (int64_t)m * p.K + kbase;
+      for (int kc = threadIdx.x; kc < ksz8; kc += 256) {
+        float v[8];
+        load8_as_float(p.x, p.x_dtype, row + kc * 8, v);
+        if (p.input_scale) {
+          float sc8[8];
+          load8_as_float(p.input_scale, B200WOQ_F32, kbase + kc * 8, sc8);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + u * blockDim.x;
-        if (c < cnt) {
-          const int m = c / ksz8, kc = c - m * ksz8;
-          load8_as_float(p.x, p.x_dtype, (int64_t)m * p.K + kbase + kc * 8, v[u]);
+          for (int i = 0; i < 8; ++i) v[i] *= sc8[i];
         }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int c = c0 + u * blockDim.x;
-        if (c < cnt) {
-          const int m = c / ksz8, kc = c - m * ksz8;
-          if (p.input_scale) {
-            float sc8[8];
-            load8_as_float(p.input_scale, B200WOQ_F32, kbase + kc * 8, sc8);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[u][i] *= sc8[i];
-          }
-          *reinterpret_cast<uint4*>(xs + m * p.xs_ld + kc * 8) = permute_pack8<BITS>(v[u]);
-        }
+        *reinterpret_cast<uint4*>(xs + m * p.xs_ld + kc * 8) = permute_pack8<BITS>(v);
       }
     }
   }
@@ -271,9 +271,24 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   __syncthreads();
   // let the next kernel in the stream start its own (constant) weight prefetch while we compute
   if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (SUB) {  // X_g[m] = sum of the (fp16-rounded) activations of each group, fp32
+    const int ng = ge - gb;
+    for (int task = warp; task < (int)p.M * ng; task += 8) {
+      const int m = task / ng, gl = task - m * ng;
+      float sum = 0.f;
+      for (int e = lane * 4; e < g; e += 128) {
+        const uint2 v = *reinterpret_cast<const uint2*>(xs + m * p.xs_ld + gl * g + e);
+        const float2 a = __half22float2(u32_as_h2(v.x)), b = __half22float2(u32_as_h2(v.y));
+        sum += (a.x + a.y) + (b.x + b.y);
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) xsum[m * p.gmax + gl] = sum;
+    }
+    __syncthreads();
+  }
 
   float acc[2][MT][4];
-  float accg[2][MT][4];  // POST only: per-group partial sums (dead code otherwise)
+  float accg[2][MT][4];  // SUB only: per-group partial sums (dead code otherwise)
 #pragma unroll
   for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -285,94 +300,142 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
       }
 
   __half2 zc[4], zn[4], sh[4];
-  float sf[4];
+  float sf[4], zf[4];
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     zc[r] = zn[r] = sh[r] = __float2half2_rn(0.f);
-    sf[r] = 0.f;
+    sf[r] = zf[r] = 0.f;
   }
-  const int zshift = (BITS == 4) ? (int)((n0 & 7) * 4) : 0;
-  const int n_in_tile = strip * 32 + 4 * gq;
-  int i_in_g = 0, gl = g0 - gb;
+  const int zshift = (BITS == 4) ? ((n0 & 7) * 4) : 0;
+  int gl = g0 - gb;
   int xoff = (g0 - gb) * g + t * KPW;  // halves; advances by 4*KPW per iteration
 
-  for (int base = 0; base < total; base += kPrefetch) {
+  auto group_start = [&]() {
+    const uint2 sc = *reinterpret_cast<const uint2*>(sc_s + gl * 128 + n_in_tile);
+    const uint32_t zw = zr_s[gl * ZW + n_in_tile / KPW] >> zshift;
+    const __half2 s01 = u32_as_h2(sc.x), s23 = u32_as_h2(sc.y);
+    const __half sr[4] = {__low2half(s01), __high2half(s01), __low2half(s23), __high2half(s23)};
 #pragma unroll
-    for (int j = 0; j < kPrefetch; ++j) {
-      const int it = base + j;
-      if (it < total) {
+    for (int r = 0; r < 4; ++r) {
+      // stored zp-1, +1 wraps to 0 past the maximum (modules.py:363, 409-410)
+      const uint32_t z = (((zw >> (BITS * r)) & ((1u << BITS) - 1u)) + 1u) & ((1u << BITS) - 1u);
+      sf[r] = __half2float(sr[r]);
+      if (SUB) {
+        zf[r] = (float)z;
+      } else {
+        zc[r] = __float2half2_rn(1024.f + (float)z);
+        zn[r] = __float2half2_rn(-(64.f + (float)z));
+        sh[r] = __half2half2(sr[r]);
+      }
+    }
+  };
+  auto do_iter = [&](const int4 wv) {
+    uint32_t P[4][4];
+    const uint32_t wr[4] = {(uint32_t)wv.x, (uint32_t)wv.y, (uint32_t)wv.z, (uint32_t)wv.w};
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      if (SUB) {
+        P[r][0] = wr[r] & 0x000f000fu;
+        P[r][1] = (wr[r] >> 4) & 0x000f000fu;
+        P[r][2] = (wr[r] >> 8) & 0x000f000fu;
+        P[r][3] = (wr[r] >> 12) & 0x000f000fu;
+      } else {
+        __half2 h[4];
+        Dequant<BITS>::run(wr[r], zc[r], zn[r], h);
+#pragma unroll
+        for (int q = 0; q < Dequant<BITS>::kPairs; ++q) P[r][q] = h2_as_u32(__hmul2(h[q], sh[r]));
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const int m = gq + 8 * mt;
+      uint32_t xb[4] = {0u, 0u, 0u, 0u};
+      if (m < p.M) {
+        if (BITS == 4) {
+          const uint4 v = *reinterpret_cast<const uint4*>(xs + m * p.xs_ld + xoff);
+          xb[0] = v.x; xb[1] = v.y; xb[2] = v.z; xb[3] = v.w;
+        } else {
+          const uint2 v = *reinterpret_cast<const uint2*>(xs + m * p.xs_ld + xoff);
+          xb[0] = v.x; xb[1] = v.y;
+        }
+      }
+#pragma unroll
+      for (int st = 0; st < NSTEP; ++st) {
+        if (SUB) {
+          mma_16816(accg[0][mt], P[0][2 * st], P[1][2 * st], P[0][2 * st + 1], P[1][2 * st + 1], xb[2 * st], xb[2 * st + 1]);
+          mma_16816(accg[1][mt], P[2][2 * st], P[3][2 * st], P[2][2 * st + 1], P[3][2 * st + 1], xb[2 * st], xb[2 * st + 1]);
+        } else {
+          mma_16816(acc[0][mt], P[0][2 * st], P[1][2 * st], P[0][2 * st + 1], P[1][2 * st + 1], xb[2 * st], xb[2 * st + 1]);
+          mma_16816(acc[1][mt], P[2][2 * st], P[3][2 * st], P[2][2 * st + 1], P[3][2 * st + 1], xb[2 * st], xb[2 * st + 1]);
+        }
+      }
+    }
+    xoff += 4 * KPW;
+  };
+  auto group_end = [&]() {
+    if (SUB) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int m0 = 8 * mt + 2 * t;
+        const float x0 = (m0 < p.M) ? xsum[m0 * p.gmax + gl] : 0.f;
+        const float x1 = (m0 + 1 < p.M) ? xsum[(m0 + 1) * p.gmax + gl] : 0.f;
+#pragma unroll
+        for (int tile = 0; tile < 2; ++tile) {
+          const float sa = sf[2 * tile], sb = sf[2 * tile + 1], za = zf[2 * tile], zb = zf[2 * tile + 1];
+          acc[tile][mt][0] = fmaf(fmaf(accg[tile][mt][0], 16777216.f, -za * x0), sa, acc[tile][mt][0]);
+          acc[tile][mt][1] = fmaf(fmaf(accg[tile][mt][1], 16777216.f, -za * x1), sa, acc[tile][mt][1]);
+          acc[tile][mt][2] = fmaf(fmaf(accg[tile][mt][2], 16777216.f, -zb * x0), sb, acc[tile][mt][2]);
+          acc[tile][mt][3] = fmaf(fmaf(accg[tile][mt][3], 16777216.f, -zb * x1), sb, acc[tile][mt][3]);
+          accg[tile][mt][0] = accg[tile][mt][1] = accg[tile][mt][2] = accg[tile][mt][3] = 0.f;
+        }
+      }
+    }
+    ++gl;
+  };
+
+  int it_load = kPrefetch;  // next iteration whose words get loaded into the ring
+  if (NI == 4) {            // group_size 128 (4-bit): two groups per pass over the 8-deep ring, no per-iteration tests
+    const int ngw = total / 4;
+    for (int gi = 0; gi < ngw; gi += 2) {
+      group_start();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
         const int4 wv = buf[j];
-        if (it + kPrefetch < total) buf[j] = ldg_nc_v4(wptr);
+        if (it_load < total) buf[j] = ldg_nc_v4(wptr);
         wptr += wstep;
-        if (i_in_g == 0) {
-          const uint2 sc = *reinterpret_cast<const uint2*>(sc_s + gl * 128 + n_in_tile);
-          const uint32_t zw = zr_s[gl * ZW + n_in_tile / KPW] >> zshift;
-          const __half2 s01 = u32_as_h2(sc.x), s23 = u32_as_h2(sc.y);
-          const __half sr[4] = {__low2half(s01), __high2half(s01), __low2half(s23), __high2half(s23)};
+        ++it_load;
+        do_iter(wv);
+      }
+      group_end();
+      if (gi + 1 < ngw) {
+        group_start();
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            uint32_t z = ((zw >> (BITS * r)) & ((1u << BITS) - 1u)) + 1u;  // stored zp-1 (modules.py:363)
-            if (z > ((1u << BITS) - 1u)) z = 0;                              // modules.py:409-410
-            zc[r] = __float2half2_rn(1024.f + (float)z);
-            zn[r] = __float2half2_rn(-(64.f + (float)z));
-            sh[r] = __half2half2(sr[r]);
-            sf[r] = __half2float(sr[r]);
-          }
+        for (int j = 4; j < 8; ++j) {
+          const int4 wv = buf[j];
+          if (it_load < total) buf[j] = ldg_nc_v4(wptr);
+          wptr += wstep;
+          ++it_load;
+          do_iter(wv);
         }
-        __half2 P[4][4];
-        Dequant<BITS>::run((uint32_t)wv.x, zc[0], zn[0], P[0]);
-        Dequant<BITS>::run((uint32_t)wv.y, zc[1], zn[1], P[1]);
-        Dequant<BITS>::run((uint32_t)wv.z, zc[2], zn[2], P[2]);
-        Dequant<BITS>::run((uint32_t)wv.w, zc[3], zn[3], P[3]);
-        if (!POST) {
+        group_end();
+      }
+    }
+  } else {
+    int i_in_g = 0;
+    for (int base = 0; base < total; base += kPrefetch) {
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-#pragma unroll
-            for (int q = 0; q < Dequant<BITS>::kPairs; ++q) P[r][q] = __hmul2(P[r][q], sh[r]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int m = gq + 8 * mt;
-          uint32_t xb[4] = {0u, 0u, 0u, 0u};
-          if (m < p.M) {
-            if (BITS == 4) {
-              const uint4 v = *reinterpret_cast<const uint4*>(xs + m * p.xs_ld + xoff);
-              xb[0] = v.x; xb[1] = v.y; xb[2] = v.z; xb[3] = v.w;
-            } else {
-              const uint2 v = *reinterpret_cast<const uint2*>(xs + m * p.xs_ld + xoff);
-              xb[0] = v.x; xb[1] = v.y;
-            }
-          }
-#pragma unroll
-          for (int st = 0; st < NSTEP; ++st) {
-            if (POST) {
-              mma_16816(accg[0][mt], h2_as_u32(P[0][2 * st]), h2_as_u32(P[1][2 * st]), h2_as_u32(P[0][2 * st + 1]),
-                        h2_as_u32(P[1][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
-              mma_16816(accg[1][mt], h2_as_u32(P[2][2 * st]), h2_as_u32(P[3][2 * st]), h2_as_u32(P[2][2 * st + 1]),
-                        h2_as_u32(P[3][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
-            } else {
-              mma_16816(acc[0][mt], h2_as_u32(P[0][2 * st]), h2_as_u32(P[1][2 * st]), h2_as_u32(P[0][2 * st + 1]),
-                        h2_as_u32(P[1][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
-              mma_16816(acc[1][mt], h2_as_u32(P[2][2 * st]), h2_as_u32(P[3][2 * st]), h2_as_u32(P[2][2 * st + 1]),
-                        h2_as_u32(P[3][2 * st + 1]), xb[2 * st], xb[2 * st + 1]);
-            }
-          }
-        }
-        xoff += 4 * KPW;
-        if (++i_in_g == NI) {
-          i_in_g = 0;
-          ++gl;
-          if (POST) {
-#pragma unroll
-            for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                acc[tile][mt][0] = fmaf(accg[tile][mt][0], sf[2 * tile], acc[tile][mt][0]);
-                acc[tile][mt][1] = fmaf(accg[tile][mt][1], sf[2 * tile], acc[tile][mt][1]);
-                acc[tile][mt][2] = fmaf(accg[tile][mt][2], sf[2 * tile + 1], acc[tile][mt][2]);
-                acc[tile][mt][3] = fmaf(accg[tile][mt][3], sf[2 * tile + 1], acc[tile][mt][3]);
-                accg[tile][mt][0] = accg[tile][mt][1] = accg[tile][mt][2] = accg[tile][mt][3] = 0.f;
-              }
+      for (int j = 0; j < kPrefetch; ++j) {
+        const int it = base + j;
+        if (it < total) {
+          const int4 wv = buf[j];
+          if (it_load < total) buf[j] = ldg_nc_v4(wptr);
+          wptr += wstep;
+          ++it_load;
+          if (i_in_g == 0) group_start();
+          do_iter(wv);
+          if (++i_in_g == NI) {
+            i_in_g = 0;
+            group_end();
           }
         }
       }
@@ -382,58 +445,39 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   // ---- epilogue ----
   // lane holds y[m = 8mt + 2t + {0,1}][n0 + {0,1,2,3}]:
   // acc[tile][mt][c]: c0,c1 -> row gq (n0 + 2*tile), cols 2t,2t+1 ; c2,c3 -> row gq+8 (n0 + 2*tile + 1)
-  __syncthreads();  // xs / sc_s / zr_s no longer needed; k-half exchange reuses the xs region
-  float* kred = reinterpret_cast<float*>(xs);  // [4 strips][MT][32 lanes][8]
-  if (khalf == 1) {
-#pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      float* dst = kred + (((strip * MT + mt) * 32 + lane) * 8);
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) dst[tile * 4 + c] = acc[tile][mt][c];
-    }
-  }
-  __syncthreads();
-  // columns of the tile are owned by cluster ranks in slices of 128/S; write the CTA partial of each slice into
-  // its owner's `red` ([src rank][m][128/S]) through distributed shared memory
+  // columns of the tile are owned by cluster ranks in slices of 128/S; every warp writes its partial of a slice
+  // into the owner's `red` ([source = 2*rank + khalf][m][128/S]) through distributed shared memory
   const int slice = 128 / S;
   if (S > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  if (khalf == 0 && strip_valid) {
+  if (strip_valid) {
     const int owner = n_in_tile / slice;
     float* owner_red = (S == 1) ? red : cluster.map_shared_rank(red, owner);
+    const int src = 2 * rank + khalf;
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt) {
-      const float* src = kred + (((strip * MT + mt) * 32 + lane) * 8);
-#pragma unroll
-      for (int tile = 0; tile < 2; ++tile)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[tile][mt][c] += src[tile * 4 + c];
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int m = 8 * mt + 2 * t + half;
         if (m < p.M) {
           // n0+0: tile0 c(half) ; n0+1: tile0 c(2+half) ; n0+2: tile1 c(half) ; n0+3: tile1 c(2+half)
           const float4 v = make_float4(acc[0][mt][half], acc[0][mt][2 + half], acc[1][mt][half], acc[1][mt][2 + half]);
-          *reinterpret_cast<float4*>(owner_red + ((size_t)rank * p.M + m) * slice + (n_in_tile - owner * slice)) = v;
+          *reinterpret_cast<float4*>(owner_red + ((size_t)src * p.M + m) * slice + (n_in_tile - owner * slice)) = v;
         }
       }
-    }
   }
   if (S > 1) cluster.sync(); else __syncthreads();
   {
-    const int64_t nbase = n_tile0 + (int64_t)rank * slice;
-    const int cnt = (int)p.M * slice;
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
-      const int m = i / slice, nl = i - m * slice;
-      const int64_t n = nbase + nl;
-      if (n < N) {
-        float sum = 0.f;
-        for (int sp = 0; sp < S; ++sp) sum += red[((size_t)sp * p.M + m) * slice + nl];
-        if (p.bias) sum += load_as_float(p.bias, p.bias_dtype, n);
-        store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, sum);
+    const int nbase = n_tile0 + rank * slice;
+    for (int m = 0; m < (int)p.M; ++m)
+      for (int nl = threadIdx.x; nl < slice; nl += 256) {
+        const int n = nbase + nl;
+        if (n < N) {
+          float sum = 0.f;
+          for (int sp = 0; sp < 2 * S; ++sp) sum += red[((size_t)sp * p.M + m) * slice + nl];
+          if (p.bias) sum += load_as_float(p.bias, p.bias_dtype, n);
+          store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, sum);
+        }
       }
-    }
   }
 }
 
@@ -506,12 +550,12 @@ static int choose_split(int64_t M, int64_t N, int64_t K, int g) {
 
 static size_t fast_smem_bytes(int64_t Mc, int mt, int64_t gmax, int g, int bits) {
   const int kpw = 32 / bits;
-  const size_t red = (size_t)Mc * 128 * sizeof(float);
-  size_t xs = (size_t)Mc * (gmax * g + 32) * sizeof(__half);
-  const size_t kred = (size_t)4 * mt * 32 * 8 * sizeof(float);
-  if (xs < kred) xs = kred;
+  const size_t red = (size_t)2 * Mc * 128 * sizeof(float);
+  const size_t xs = (size_t)Mc * (gmax * g + 32) * sizeof(__half);
+  const size_t xsum = (size_t)Mc * gmax * sizeof(float);
   const size_t sc = (size_t)gmax * 128 * sizeof(__half), zr = (size_t)gmax * (128 / kpw) * sizeof(uint32_t);
-  return red + xs + sc + zr + 64;
+  (void)mt;
+  return red + xs + xsum + sc + zr + 64;
 }
 
 }  // namespace b200woq
@@ -565,9 +609,10 @@ static int launch_fast(GemmParams& p, int64_t Mc, cudaStream_t st) {
     WOQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));                                                            \
     count_launch(1);                                                                                        \
   } while (0)
+  constexpr bool kSub = (BITS == 4);  // subnormal-code path for the small-batch 4-bit kernels
   switch (mt) {
-    case 1: WOQ_LAUNCH(1, true); break;
-    case 2: WOQ_LAUNCH(2, false); break;
+    case 1: WOQ_LAUNCH(1, kSub); break;
+    case 2: WOQ_LAUNCH(2, kSub); break;
     case 4: WOQ_LAUNCH(4, false); break;
     default: WOQ_LAUNCH(8, false); break;
   }

@@ -1,0 +1,52 @@
+"""Host-side logic of the N>1 path, on CPU with gloo (world_size 2): sample sharding and the Hessian all-reduce
+that makes every rank hold the same (2/n) * sum_j X_j^T X_j.  The compute on the ranks is the oracle
+(tests may use it as the checker/stand-in; the product path uses the CUDA kernels)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from neural_compressor_b200.algorithms.gptq import _HessianBank, shard_range
+
+    g = torch.Generator().manual_seed(7)
+    X = [torch.randn(1, 16, 24, generator=g) for _ in range(6)]  # same data on every rank
+    lo, hi = shard_range(len(X), rank, world)
+    bank = _HessianBank(torch.device("cpu"))
+    bank.acc.append(torch.zeros(24, 24))
+    for x in X[lo:hi]:
+        x2 = x.reshape(-1, 24)
+        bank.acc[0] += x2.t() @ x2
+        bank.nsamples += 1
+    bank.all_reduce()
+    ref = sum(x.reshape(-1, 24).t() @ x.reshape(-1, 24) for x in X)
+    ok = bank.nsamples == len(X) and torch.allclose(bank.acc[0], ref, rtol=1e-5, atol=1e-5)
+    gathered = [torch.zeros(24, 24) for _ in range(world)]
+    dist.all_gather(gathered, bank.acc[0])
+    ok = ok and all(torch.equal(gathered[0], t) for t in gathered)  # every rank holds the identical Hessian
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_shard_range_partitions_everything():
+    from neural_compressor_b200.algorithms.gptq import shard_range
+
+    for n in (1, 7, 128):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def test_hessian_all_reduce_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29512 + os.getpid() % 200
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

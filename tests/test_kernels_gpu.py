@@ -160,6 +160,28 @@ def test_hessian_accumulate_vs_fp64(ops, dtype, T, C):
     assert torch.equal(H, H.t())
 
 
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("T,C", [(200, 256), (513, 384), (64, 40), (1000, 1032), (4096, 2048)])
+def test_hessian_tcgen05_kernel(ops, dtype, T, C, monkeypatch):
+    """The tcgen05/TMA/TMEM SYRK (hessian_tc.cu) against fp64 and against the mma.sync kernel."""
+    gen = torch.Generator().manual_seed(T * 3 + C)
+    X = (torch.randn(T, C, generator=gen) * (1 + 5 * (torch.arange(C) % 7 == 0))).to(dtype).to(DEV)
+
+    def run(impl, reps):
+        monkeypatch.setenv("B200WOQ_HESSIAN_IMPL", impl)
+        H = torch.zeros(C, C, dtype=torch.float32, device=DEV)
+        for _ in range(reps):
+            ops.hessian_accumulate(X, H)
+        return ops.hessian_finalize(H, nsamples=2, percdamp=0.0)[0]
+
+    Htc, Hmma = run("tc", 2), run("mma", 2)
+    ref = (X.double().t() @ X.double()) * 2.0
+    scale = ref.abs().max().item()
+    assert (Htc.double() - ref).abs().max().item() / scale < 1e-5
+    assert (Htc - Hmma).abs().max().item() / scale < 1e-5
+    assert torch.equal(Htc, Htc.t())
+
+
 def test_hessian_finalize_dead_and_damp(ops, golden_gptq):
     X = golden_gptq["X"]
     C = X[0].shape[-1]

@@ -73,7 +73,14 @@ def bench_hessian(out):
             T = 2048 * 8
             X = torch.randn(T, C, device=DEV, dtype=dt)
             H = torch.zeros(C, C, device=DEV)
+            import os
+            os.environ["B200WOQ_HESSIAN_IMPL"] = "tc"
+            ms_tc = time_cuda(lambda: ops.hessian_accumulate(X, H), iters=5, warmup=2)
+            os.environ["B200WOQ_HESSIAN_IMPL"] = "mma"
             ms = time_cuda(lambda: ops.hessian_accumulate(X, H), iters=5, warmup=2)
+            res.append(dict(C=C, dtype=str(dt), T=T, tc_ms=ms_tc, tc_tflops_sym_half=T * C * (C + 128) / ms_tc / 1e9,
+                            tc_tflops_full_equiv=2 * T * C * C / ms_tc / 1e9))
+            print(res[-1], file=sys.stderr)
             fl_full = 2 * T * C * C
             nt = math.ceil(C / 128)
             fl_done = 2 * T * 128 * 128 * nt * (nt + 1) / 2
