@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   float* red = reinterpret_cast<float*>(smem_raw);
   __half* xs = reinterpret_cast<__half*>(smem_raw + (size_t)2 * p.M * 128 * sizeof(float));
   float* xsum = reinterpret_cast<float*>(xs + (size_t)p.M * p.xs_ld);
-  __half* sc_s = reinterpret_cast<__half*>(xsum + (size_t)p.M * p.gmax);
+  __half* sc_s = reinterpret_cast<__half*>(xsum + (((size_t)p.M * p.gmax + 3) & ~(size_t)3));  // keep 16-byte alignment
   uint32_t* zr_s = reinterpret_cast<uint32_t*>(sc_s + (size_t)p.gmax * 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -552,7 +552,7 @@ static size_t fast_smem_bytes(int64_t Mc, int mt, int64_t gmax, int g, int bits)
   const int kpw = 32 / bits;
   const size_t red = (size_t)2 * Mc * 128 * sizeof(float);
   const size_t xs = (size_t)Mc * (gmax * g + 32) * sizeof(__half);
-  const size_t xsum = (size_t)Mc * gmax * sizeof(float);
+  const size_t xsum = (((size_t)Mc * gmax + 3) & ~(size_t)3) * sizeof(float);
   const size_t sc = (size_t)gmax * 128 * sizeof(__half), zr = (size_t)gmax * (128 / kpw) * sizeof(uint32_t);
   (void)mt;
   return red + xs + xsum + sc + zr + 64;
