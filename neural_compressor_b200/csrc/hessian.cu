@@ -18,7 +18,7 @@
 
 namespace b200woq {
 
-constexpr bool kHessianDefaultTc = false;  // flipped once the tcgen05 kernel is parity-green on hardware
+constexpr bool kHessianDefaultTc = true;  // tcgen05 kernel is the default (parity-green on B200); mma.sync kept as fallback
 constexpr int HT = 128;      // output tile edge
 constexpr int HBK = 32;      // tokens per pipeline stage
 constexpr int HLD = HT + 8;  // padded smem row (halves): 272 B rows -> conflict-free ldmatrix

@@ -8,6 +8,10 @@
 //
 //   tile        128 (i) x 256 (j) fp32 accumulator = 256 TMEM columns, one CTA per tile, tiles with 128-row block
 //               ti <= 2*tj+1 only (SYRK: upper block triangle, the rest is mirrored in b200woq_hessian_finalize)
+//   precision   the tensor core adds into its fp32 accumulator with truncation, so a long contraction drifts
+//               (measured 1.3e-5 relative after 8192 tokens).  The token loop is therefore cut into SEGMENTS of 2048
+//               tokens; each segment accumulates in its own TMEM buffer (2 x 256 columns, double buffered) and is
+//               added to the fp32 H in global memory with round-to-nearest while the next segment's MMAs run.
 //   pipeline    4 stages x (A: 2 boxes, B: 4 boxes) = 48 KB per stage, mbarrier full/empty ring
 //   warp roles  warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer (1 lane), warps 2-5 = epilogue
 //   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16, both operands MN-major, fp32 accumulate
@@ -30,7 +34,9 @@ constexpr int A_BYTES = (TM / 64) * BOX_BYTES; // 16 KB
 constexpr int B_BYTES = (TN / 64) * BOX_BYTES; // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;
+constexpr int NUM_EPI_THREADS = 128;
+constexpr int TMEM_COLS = 512;      // two 128x256 fp32 accumulators
+constexpr int SEG_KB = 32;          // k-blocks (of BK tokens) per accumulation segment = 2048 tokens
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -100,8 +106,9 @@ __global__ void __launch_bounds__(192, 1)
   const uint32_t bars = base + STAGES * STAGE_BYTES;            // full[S], empty[S], accum, tmem slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  const uint32_t accum_bar = bars + 8u * (2 * STAGES);
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 1);
+  auto accum_full = [&](int b) { return bars + 8u * (2 * STAGES + b); };       // MMA -> epilogue
+  auto accum_empty = [&](int b) { return bars + 8u * (2 * STAGES + 2 + b); };  // epilogue -> MMA
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -113,7 +120,10 @@ __global__ void __launch_bounds__(192, 1)
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    mbar_init(accum_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accum_full(b), 1);
+      mbar_init(accum_empty(b), NUM_EPI_THREADS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -144,50 +154,66 @@ __global__ void __launch_bounds__(192, 1)
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int kb = 0; kb < nk; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(full_bar(s), ph);
+      const int nseg = (nk + SEG_KB - 1) / SEG_KB;
+      for (int seg = 0; seg < nseg; ++seg) {
+        const int b = seg & 1;
+        // wait until the epilogue has drained this buffer (first use of each buffer passes immediately)
+        mbar_wait(accum_empty(b), ((uint32_t)(seg >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * STAGE_BYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * TN);
+        const int kb1 = min(nk, (seg + 1) * SEG_KB);
+        for (int kb = seg * SEG_KB; kb < kb1; ++kb) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * STAGE_BYTES;
 #pragma unroll
-        for (int k4 = 0; k4 < BK / 16; ++k4) {
-          const uint64_t ad = make_desc(sa + k4 * 2048);            // 16 tokens = 2 groups of 8 x 128 B rows
-          const uint64_t bd = make_desc(sa + A_BYTES + k4 * 2048);
-          umma_f16(tmem_base, ad, bd, idesc, (kb | k4) != 0 ? 1u : 0u);
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            const uint64_t ad = make_desc(sa + k4 * 2048);            // 16 tokens = 2 groups of 8 x 128 B rows
+            const uint64_t bd = make_desc(sa + A_BYTES + k4 * 2048);
+            umma_f16(tmem_d, ad, bd, idesc, (kb != seg * SEG_KB || k4 != 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar(s));  // frees the smem stage when these MMAs retire
+        umma_commit(accum_full(b));   // this segment's accumulator is complete
       }
-      umma_commit(accum_bar);       // accumulator complete
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32); H tile += segment accumulator (round-to-nearest adds)
     const int q = warp & 3;
     const int64_t row = i0 + q * 32 + lane;
+    const int nseg = (nk + SEG_KB - 1) / SEG_KB;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int b = seg & 1;
+      mbar_wait(accum_full(b), (uint32_t)(seg >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-    for (int cc = 0; cc < TN / 32; ++cc) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), r);
-      const int64_t col0 = j0 + cc * 32;
-      if (row < C && col0 < C) {
-        float* dst = H + row * C + col0;
-        if (col0 + 32 <= C && ((C & 3) == 0)) {
+      for (int cc = 0; cc < TN / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TN + cc * 32), r);
+        const int64_t col0 = j0 + cc * 32;
+        if (row < C && col0 < C) {
+          float* dst = H + row * C + col0;
+          if (col0 + 32 <= C && ((C & 3) == 0)) {
 #pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            float4 h = *reinterpret_cast<float4*>(dst + 4 * v);
-            h.x += __uint_as_float(r[4 * v + 0]);
-            h.y += __uint_as_float(r[4 * v + 1]);
-            h.z += __uint_as_float(r[4 * v + 2]);
-            h.w += __uint_as_float(r[4 * v + 3]);
-            *reinterpret_cast<float4*>(dst + 4 * v) = h;
+            for (int v = 0; v < 8; ++v) {
+              float4 h = *reinterpret_cast<float4*>(dst + 4 * v);
+              h.x += __uint_as_float(r[4 * v + 0]);
+              h.y += __uint_as_float(r[4 * v + 1]);
+              h.z += __uint_as_float(r[4 * v + 2]);
+              h.w += __uint_as_float(r[4 * v + 3]);
+              *reinterpret_cast<float4*>(dst + 4 * v) = h;
+            }
+          } else {
+            for (int v = 0; v < 32; ++v)
+              if (col0 + v < C) dst[v] += __uint_as_float(r[v]);
           }
-        } else {
-          for (int v = 0; v < 32; ++v)
-            if (col0 + v < C) dst[v] += __uint_as_float(r[v]);
         }
       }
+      // release the TMEM buffer to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(accum_empty(b)) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
