@@ -207,7 +207,7 @@ def run_b200(args):
     if h_ms:
         ach = sum(h_fl) / (sum(h_ms) / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
-        roofline = dict(bound="tensor", kernel="hessian_syrk16_kernel", achieved=round(ach, 1), peak=peak,
+        roofline = dict(bound="tensor", kernel="hessian_syrk_tc_kernel (tcgen05 + TMA + TMEM)", achieved=round(ach, 1), peak=peak,
                         unit="TFLOP/s", frac=round(ach / peak, 4), traffic=None, peak_source=pk["source"] + ", sustained",
                         launches=len(h_ms), avg_launch_ms=round(sum(h_ms) / len(h_ms), 4),
                         share_of_step=round(sum(h_ms) / ms_total, 3),

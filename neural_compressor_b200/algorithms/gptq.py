@@ -280,6 +280,28 @@ class RAWGPTQuantizer:
             qkv, post = layers[0:3], layers[3:]
         return [qkv] + [[l] for l in post]
 
+    def _fasterquant_rows_sharded(self, W, Hinv, dead, cfg):
+        """The rows of a layer are independent given Hinv (per-row scale/zero gptq.py:1544-1565, per-row updates
+        :1297-1304), so with several ranks each one runs the column loop on N/world rows and the codes,
+        scales, zeros and fake-quant weights are all-gathered (NCCL).  Bit-identical to the un-sharded result."""
+        import torch.distributed as dist
+
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        N = W.shape[0]
+        if world == 1 or N % world != 0:
+            return ops.gptq_fasterquant(W, Hinv, dead, cfg["block_size"], cfg["group_size"], cfg["bits"], cfg["sym"],
+                                        cfg["mse"])
+        rank = dist.get_rank()
+        rows = N // world
+        part = ops.gptq_fasterquant(W[rank * rows:(rank + 1) * rows].contiguous(), Hinv, dead, cfg["block_size"],
+                                    cfg["group_size"], cfg["bits"], cfg["sym"], cfg["mse"])
+        out = {}
+        for k, v in part.items():
+            full = torch.empty((N,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
+            dist.all_gather_into_tensor(full, v.contiguous())
+            out[k] = full
+        return out
+
     def _sync_time(self, key, t0):
         if self.profile:
             torch.cuda.synchronize()
@@ -359,8 +381,7 @@ class RAWGPTQuantizer:
                 W = layer.weight.data
                 W = (W.t() if _is_conv1d(layer) else W).float()
                 W = (W[:, perm] if perm is not None else W).contiguous().clone()
-                r = ops.gptq_fasterquant(W, Hinv, dead, cfg["block_size"], cfg["group_size"], cfg["bits"], cfg["sym"],
-                                         cfg["mse"])
+                r = self._fasterquant_rows_sharded(W, Hinv, dead, cfg)
                 if perm is not None:
                     inv = torch.argsort(perm)
                     r["Q"] = r["Q"][:, inv].contiguous()

@@ -22,7 +22,7 @@
 namespace b200woq {
 
 constexpr int SUB = 128;  // columns per register-resident sub-block
-constexpr int RW = 2;     // rows per warp (interleaved for ILP); N/2 warps keep every SM busy
+constexpr int RW = 4;     // rows per warp: 4 independent dependency chains interleave in one warp
 
 // Correctly rounded fp32 division by a divisor that is reused many times (Markstein 1990): with r = RN(1/d),
 // q0 = RN(a*r), rem = a - q0*d (exact in one FMA), RN(q0 + rem*r) == RN(a/d) unless d's significand is all ones
@@ -120,16 +120,31 @@ __global__ void zero_dead_columns_kernel(float* __restrict__ W, int64_t N, int64
     if (dead[i % C]) W[i] = 0.f;
 }
 
-// column loop over one sub-block [c0, c0+ncols), ncols <= 128
-__global__ void __launch_bounds__(256)
+// column loop over one sub-block [c0, c0+ncols), ncols <= 128.
+// CTA = 4 warps x RW rows.  Per-column constants (d = Hinv[i,i], RN(1/d), 0.5/d^2, "needs IEEE division" flag) are
+// computed once per CTA into shared memory, so the serial loop body is ~30 instructions per (column, row).
+// Err is written TRANSPOSED (ErrT[col_in_block][row]) so the lazy-update GEMM reads it coalesced.
+__global__ void __launch_bounds__(128)
     gptq_subblock_kernel(float* __restrict__ W, const float* __restrict__ Hinv, int64_t N, int64_t C, int64_t c0,
                          int ncols, int g, int64_t G, float maxq, const float* __restrict__ scale,
                          const float* __restrict__ zero, uint8_t* __restrict__ codes, float* __restrict__ Q,
-                         float* __restrict__ Err, int64_t err_ld, int64_t err_col0, float* __restrict__ losses) {
-  extern __shared__ float hs[];  // [ncols][SUB+1] upper-triangular diagonal block of Hinv
+                         float* __restrict__ ErrT, int64_t err_col0, float* __restrict__ losses) {
+  extern __shared__ float hs[];  // [ncols][SUB+1] upper-triangular diagonal block of Hinv, then 4 x [SUB] column constants
+  float* dcol = hs + SUB * (SUB + 1);
+  float* rcol = dcol + SUB;
+  float* lcol = rcol + SUB;
+  uint32_t* fcol = reinterpret_cast<uint32_t*>(lcol + SUB);
   for (int e = threadIdx.x; e < ncols * SUB; e += blockDim.x) {
     const int r = e / SUB, c = e % SUB;
     hs[r * (SUB + 1) + c] = (c < ncols && c >= r) ? Hinv[(c0 + r) * C + c0 + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
+    const float d = Hinv[(c0 + i) * C + c0 + i];
+    const RnDivisor D = make_divisor(d);
+    dcol[i] = d;
+    rcol[i] = D.r;
+    lcol[i] = __fdividef(0.5f, d * d);
+    fcol[i] = D.slow ? 1u : 0u;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -152,56 +167,64 @@ __global__ void __launch_bounds__(256)
       ev[r][s] = 0.f;
     }
   }
-  float sc[RW], zr[RW];
-  RnDivisor dsc[RW];
+  float sc[RW], zr[RW], rs[RW];
+  bool sslow[RW];
   const bool per_channel = (g <= 0);
-  {  // parameters of the group that contains the first column (it may have started in an earlier sub-block)
-    const int64_t gi_first = per_channel ? 0 : c0 / g;
+  auto load_group = [&](int64_t gi) {
 #pragma unroll
     for (int r = 0; r < RW; ++r) {
       const int64_t n = (row0 + r < N) ? row0 + r : N - 1;
-      sc[r] = scale[n * G + gi_first];
-      zr[r] = zero[n * G + gi_first];
-      dsc[r] = make_divisor(sc[r]);
+      sc[r] = scale[n * G + gi];
+      zr[r] = zero[n * G + gi];
+      const RnDivisor D = make_divisor(sc[r]);
+      rs[r] = D.r;
+      sslow[r] = D.slow;
     }
-  }
+  };
+  load_group(per_channel ? 0 : c0 / g);  // the group containing the first column may have started earlier
   int next_group_col = per_channel ? INT_MAX : (int)(((c0 + g - 1) / g) * g - c0);  // first group start >= c0
-  const bool want_loss = (losses != nullptr);
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
+#pragma unroll 1
     for (int l = 0; l < 32; ++l) {
       const int i = 32 * s + l;
       if (i >= ncols) break;
       if (i == next_group_col) {  // gptq.py:1264-1272
-        const int64_t gi = (c0 + i) / g;
-#pragma unroll
-        for (int r = 0; r < RW; ++r) {
-          const int64_t n = (row0 + r < N) ? row0 + r : N - 1;
-          sc[r] = scale[n * G + gi];
-          zr[r] = zero[n * G + gi];
-          dsc[r] = make_divisor(sc[r]);
-        }
+        load_group((c0 + i) / g);
         next_group_col += g;
       }
-      const float d = hs[i * (SUB + 1) + i];
-      const RnDivisor dd = make_divisor(d);
-      const float inv_d2h = want_loss ? __fdividef(0.5f, d * d) : 0.f;
+      const float d = dcol[i], rd = rcol[i], ld = lcol[i];
+      const bool dslow = fcol[i] != 0u;
       float h[4];
 #pragma unroll
       for (int s2 = 0; s2 < 4; ++s2) h[s2] = hs[i * (SUB + 1) + lane + 32 * s2];
 #pragma unroll
       for (int r = 0; r < RW; ++r) {
         const float wi = __shfl_sync(0xffffffffu, w[r][s], l);
+        // x / scale, correctly rounded (Markstein); IEEE division for the flagged divisors
+        float t0;
+        if (sslow[r]) {
+          t0 = __fdiv_rn(wi, sc[r]);
+        } else {
+          const float q0 = __fmul_rn(wi, rs[r]);
+          t0 = __fmaf_rn(__fmaf_rn(-q0, sc[r], wi), rs[r], q0);
+        }
         // Quantizer.quantize (gptq.py:1636-1637)
-        const float qi = fminf(fmaxf(__fadd_rn(rintf(div_rn(wi, dsc[r])), zr[r]), 0.f), maxq);
+        const float qi = fminf(fmaxf(__fadd_rn(rintf(t0), zr[r]), 0.f), maxq);
         const float q = __fmul_rn(sc[r], __fsub_rn(qi, zr[r]));
         const float diff = __fsub_rn(wi, q);
-        const float err = div_rn(diff, dd);  // gptq.py:1296
+        float err;  // (w - q) / d   gptq.py:1296
+        if (dslow) {
+          err = __fdiv_rn(diff, d);
+        } else {
+          const float e0 = __fmul_rn(diff, rd);
+          err = __fmaf_rn(__fmaf_rn(-e0, d, diff), rd, e0);
+        }
         if (lane == l) {
           qv[r][s] = q;
           ev[r][s] = err;
           cd[r] |= ((uint32_t)qi & 0xffu) << (8 * s);
-          loss[r] = fmaf(diff * diff, inv_d2h, loss[r]);  // gptq.py:1294,1303 (diagnostic, not bit-pinned)
+          loss[r] = fmaf(diff * diff, ld, loss[r]);  // gptq.py:1294,1303 (diagnostic, not bit-pinned)
         }
 #pragma unroll
         for (int s2 = 0; s2 < 4; ++s2) {
@@ -211,7 +234,7 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  // write back: quantised values replace the working columns (they are final), errors go to Err
+  // write back
 #pragma unroll
   for (int r = 0; r < RW; ++r) {
     const int64_t n = row0 + r;
@@ -222,7 +245,6 @@ __global__ void __launch_bounds__(256)
       if (c < ncols) {
         if (Q) Q[n * C + c0 + c] = qv[r][s];
         codes[n * C + c0 + c] = (uint8_t)((cd[r] >> (8 * s)) & 0xffu);
-        Err[n * err_ld + err_col0 + c] = ev[r][s];
       }
     }
     if (losses) {
@@ -230,40 +252,79 @@ __global__ void __launch_bounds__(256)
       if (lane == 0) losses[n] += tot;
     }
   }
-}
-
-// W[:, j0:j1] -= Err[:, e0:e0+KK] @ Hinv[r0:r0+KK, j0:j1]   (fp32 FFMA tiles: 128 x 128, K chunks of 16)
-__global__ void __launch_bounds__(256)
-    gptq_lazy_update_kernel(float* __restrict__ W, const float* __restrict__ Err, const float* __restrict__ Hinv,
-                            int64_t N, int64_t C, int64_t err_ld, int64_t e0, int64_t r0, int KK, int64_t j0,
-                            int64_t j1) {
-  __shared__ float As[16][128 + 4];  // Err^T chunk  [k][row]
-  __shared__ float Bs[16][128 + 4];  // Hinv chunk   [k][col]
-  const int64_t n0 = (int64_t)blockIdx.y * 128, jb = j0 + (int64_t)blockIdx.x * 128;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  float acc[8][8] = {};
-  for (int k0 = 0; k0 < KK; k0 += 16) {
-    for (int e = threadIdx.x; e < 16 * 128; e += 256) {
-      {  // Err tile: coalesced along k within a row is not possible (row-major [N, ld]); read 16 k per row
-        const int row = e >> 4, k = e & 15;
-        const int64_t n = n0 + row;
-        As[k][row] = (n < N && k0 + k < KK) ? Err[n * err_ld + e0 + k0 + k] : 0.f;
-      }
-      {
-        const int k = e >> 7, c = e & 127;
-        const int64_t j = jb + c;
-        Bs[k][c] = (j < j1 && k0 + k < KK) ? Hinv[(r0 + k0 + k) * C + j] : 0.f;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int c = lane + 32 * s;
+    if (c < ncols) {
+      float* dst = ErrT + (err_col0 + c) * N + row0;
+      if (RW == 4 && row0 + 4 <= N && ((N & 3) == 0)) {
+        *reinterpret_cast<float4*>(dst) = make_float4(ev[0][s], ev[1 % RW][s], ev[2 % RW][s], ev[3 % RW][s]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+          if (row0 + r < N) dst[r] = ev[r][s];
       }
     }
+  }
+}
+
+// W[:, j0:j1] -= ErrT[e0:e0+KK, :]^T @ Hinv[r0:r0+KK, j0:j1]     exact fp32 FFMA, 128x128 tile, 8x8 per thread,
+// both operands k-major -> float4 global loads, register double buffering of the next 16-deep k chunk.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+    gptq_lazy_update_kernel(float* __restrict__ W, const float* __restrict__ ErrT, const float* __restrict__ Hinv,
+                            int64_t N, int64_t C, int64_t e0, int64_t r0, int KK, int64_t j0, int64_t j1) {
+  __shared__ __align__(16) float As[16][128];  // ErrT chunk [k][row]
+  __shared__ __align__(16) float Bs[16][128];  // Hinv chunk [k][col]
+  const int64_t n0 = (int64_t)blockIdx.y * 128, jb = j0 + (int64_t)blockIdx.x * 128;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // loader mapping: 512 float4 per operand chunk, 2 per thread
+  const int lk[2] = {(int)(threadIdx.x >> 5), (int)(threadIdx.x >> 5) + 8};
+  const int lc = (threadIdx.x & 31) * 4;
+  float4 ra[2], rb[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = k0 + lk[u];
+      ra[u] = rb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < KK) {
+        const float* pa = ErrT + (e0 + k) * N + n0 + lc;
+        const float* pb = Hinv + (r0 + k) * C + jb + lc;
+        if (VEC && n0 + lc + 3 < N) ra[u] = *reinterpret_cast<const float4*>(pa);
+        else {
+          if (n0 + lc + 0 < N) ra[u].x = pa[0];
+          if (n0 + lc + 1 < N) ra[u].y = pa[1];
+          if (n0 + lc + 2 < N) ra[u].z = pa[2];
+          if (n0 + lc + 3 < N) ra[u].w = pa[3];
+        }
+        if (VEC && jb + lc + 3 < j1) rb[u] = *reinterpret_cast<const float4*>(pb);
+        else {
+          if (jb + lc + 0 < j1) rb[u].x = pb[0];
+          if (jb + lc + 1 < j1) rb[u].y = pb[1];
+          if (jb + lc + 2 < j1) rb[u].z = pb[2];
+          if (jb + lc + 3 < j1) rb[u].w = pb[3];
+        }
+      }
+    }
+  };
+  float acc[8][8] = {};
+  gload(0);
+  for (int k0 = 0; k0 < KK; k0 += 16) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      *reinterpret_cast<float4*>(&As[lk[u]][lc]) = ra[u];
+      *reinterpret_cast<float4*>(&Bs[lk[u]][lc]) = rb[u];
+    }
     __syncthreads();
+    if (k0 + 16 < KK) gload(k0 + 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float a[8], b[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        a[u] = As[k][ty * 8 + u];
-        b[u] = Bs[k][tx + 16 * u];
-      }
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int u = 0; u < 8; ++u)
 #pragma unroll
@@ -273,12 +334,24 @@ __global__ void __launch_bounds__(256)
   }
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
-    const int64_t n = n0 + ty * 8 + u;
+    const int64_t n = n0 + (u < 4 ? ty * 4 + u : 64 + ty * 4 + (u - 4));
     if (n >= N) continue;
 #pragma unroll
-    for (int v = 0; v < 8; ++v) {
-      const int64_t j = jb + tx + 16 * v;
-      if (j < j1) W[n * C + j] -= acc[u][v];
+    for (int hv = 0; hv < 2; ++hv) {
+      const int64_t j = jb + (hv == 0 ? tx * 4 : 64 + tx * 4);
+      float* dst = W + n * C + j;
+      if (VEC && j + 3 < j1) {
+        float4 t = *reinterpret_cast<float4*>(dst);
+        t.x -= acc[u][4 * hv + 0];
+        t.y -= acc[u][4 * hv + 1];
+        t.z -= acc[u][4 * hv + 2];
+        t.w -= acc[u][4 * hv + 3];
+        *reinterpret_cast<float4*>(dst) = t;
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (j + v < j1) dst[v] -= acc[u][4 * hv + v];
+      }
     }
   }
 }
@@ -305,7 +378,7 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     set_error("gptq_fasterquant: workspace too small");
     return B200WOQ_EWORKSPACE;
   }
-  float* Err = (float*)workspace;  // [N, bs]
+  float* ErrT = (float*)workspace;  // [bs, N]  (transposed: the lazy GEMM reads it k-major)
   const float maxq = (float)((1 << bits) - 1);
   const bool per_channel = groupsize <= 0;
   const int g = per_channel ? (int)C : groupsize;
@@ -322,7 +395,8 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     zero_dead_columns_kernel<<<fp_blocks, 256, 0, st>>>(W, N, C, dead_mask);
     WOQ_LAUNCH_CHECK();
   }
-  const int rows_per_cta = 8 * RW;
+  const int rows_per_cta = 4 * RW;
+  const bool vec = ((N & 3) == 0) && ((C & 3) == 0);
   for (int64_t i1 = 0; i1 < C; i1 += bs) {
     const int64_t i2 = std::min(i1 + bs, C);
     if (!per_channel) {
@@ -336,22 +410,31 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     }
     for (int64_t c0 = i1; c0 < i2; c0 += SUB) {
       const int ncols = (int)std::min<int64_t>(SUB, i2 - c0);
-      const size_t smem = (size_t)ncols * (SUB + 1) * sizeof(float);
-      if (smem > 48 * 1024)
+      const size_t smem = ((size_t)SUB * (SUB + 1) + 4 * SUB) * sizeof(float);
+      static bool attr_set = false;
+      if (!attr_set) {
         WOQ_CUDA(cudaFuncSetAttribute(gptq_subblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      gptq_subblock_kernel<<<(unsigned)ceil_div(N, rows_per_cta), 256, smem, st>>>(
-          W, Hinv, N, C, c0, ncols, per_channel ? 0 : g, G, maxq, scale, zero, codes, Q, Err, bs, c0 - i1, losses);
+        attr_set = true;
+      }
+      gptq_subblock_kernel<<<(unsigned)ceil_div(N, rows_per_cta), 128, smem, st>>>(
+          W, Hinv, N, C, c0, ncols, per_channel ? 0 : g, G, maxq, scale, zero, codes, Q, ErrT, c0 - i1, losses);
       WOQ_LAUNCH_CHECK();
       const int64_t c1 = c0 + ncols;
       if (c1 < i2) {  // in-block propagation to the rest of the block
         dim3 grid((unsigned)ceil_div(i2 - c1, 128), (unsigned)ceil_div(N, 128));
-        gptq_lazy_update_kernel<<<grid, 256, 0, st>>>(W, Err, Hinv, N, C, bs, c0 - i1, c0, ncols, c1, i2);
+        if (vec && (c1 & 3) == 0)
+          gptq_lazy_update_kernel<true><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, c0 - i1, c0, ncols, c1, i2);
+        else
+          gptq_lazy_update_kernel<false><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, c0 - i1, c0, ncols, c1, i2);
         WOQ_LAUNCH_CHECK();
       }
     }
     if (i2 < C) {  // gptq.py:1304
       dim3 grid((unsigned)ceil_div(C - i2, 128), (unsigned)ceil_div(N, 128));
-      gptq_lazy_update_kernel<<<grid, 256, 0, st>>>(W, Err, Hinv, N, C, bs, 0, i1, (int)(i2 - i1), i2, C);
+      if (vec && (i2 & 3) == 0)
+        gptq_lazy_update_kernel<true><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, 0, i1, (int)(i2 - i1), i2, C);
+      else
+        gptq_lazy_update_kernel<false><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, 0, i1, (int)(i2 - i1), i2, C);
       WOQ_LAUNCH_CHECK();
     }
   }

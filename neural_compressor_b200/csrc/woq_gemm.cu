@@ -44,7 +44,8 @@ struct GemmParams {
   int y_dtype;
   int bits, g;
   int64_t G;
-  int S;      // split-K factor == cluster size along x
+  int S;      // split-K factor == cluster size along x (1..8)
+  int slice;  // columns of the 128-wide tile reduced by each cluster rank (multiple of 4)
   int gmax;   // max groups per CTA
   int xs_ld;  // halves per smem x row
   int pdl;
@@ -89,6 +90,7 @@ __device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_c
 __device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 
 constexpr int kPrefetch = 8;  // 16-byte loads in flight per lane
+constexpr int kRedPerM = 320; // floats of split-K exchange buffer per batch row: 2*S*slice <= 288 for S in 1..8
 
 // BITS = 4: word -> P0=(c0,c4) P1=(c1,c5) P2=(c2,c6) P3=(c3,c7) as half2 of (code - zp)
 // BITS = 8: word -> P0=(c0,c2) P1=(c1,c3)
@@ -176,7 +178,7 @@ __device__ __forceinline__ void load8_as_float(const void* base, int dtype, int6
 // and the group scale multiplies the result in fp32.  This is the exact (q-z)*scale product, i.e. slightly MORE
 // accurate than the reference's fp16-rounded weight fp16((q-z)*scale); the difference is <= 2^-11 relative per weight.
 // !SUB: codes -> (q - z) via the 0x6400 magic number, times the fp16 scale in half2 = the reference's fp16 weight.
-template <int BITS, int MT, bool SUB>
+template <int BITS, int MT, bool SUB, bool NI4>
 __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(const GemmParams p) {
   static_assert(!SUB || BITS == 4, "subnormal-code path is 4-bit only");
   constexpr int KPW = 32 / BITS;   // codes per word
@@ -186,9 +188,9 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  // smem: [ red: 2*M*128 floats ][ xs: M*xs_ld halves ][ xsum: M*gmax floats ][ sc_s: gmax*128 halves ][ zr_s ]
+  // smem: [ red: M*kRedPerM floats ][ xs: M*xs_ld halves ][ xsum: M*gmax floats ][ sc_s: gmax*128 halves ][ zr_s ]
   float* red = reinterpret_cast<float*>(smem_raw);
-  __half* xs = reinterpret_cast<__half*>(smem_raw + (size_t)2 * p.M * 128 * sizeof(float));
+  __half* xs = reinterpret_cast<__half*>(smem_raw + (size_t)p.M * kRedPerM * sizeof(float));
   float* xsum = reinterpret_cast<float*>(xs + (size_t)p.M * p.xs_ld);
   __half* sc_s = reinterpret_cast<__half*>(xsum + (((size_t)p.M * p.gmax + 3) & ~(size_t)3));  // keep 16-byte alignment
   uint32_t* zr_s = reinterpret_cast<uint32_t*>(sc_s + (size_t)p.gmax * 128);
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   const int n0 = n_tile0 + n_in_tile;
   const bool strip_valid = n_tile0 + strip * 32 < N;
   const int g = p.g;
-  const int NI = g / KSTEP;  // 16-byte loads per group per lane
+  const int NI = NI4 ? 4 : g / KSTEP;  // 16-byte loads per group per lane (NI4: group_size == 4*KSTEP)
   const int S = p.S;
   const int rank = blockIdx.x;  // == cluster rank (cluster dims = (S,1,1), gridDim.x == S)
   // all CTAs of the cluster must be resident before anyone writes into a peer's shared memory: arrive now,
@@ -394,8 +396,9 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   };
 
   int it_load = kPrefetch;  // next iteration whose words get loaded into the ring
-  if (NI == 4) {            // group_size 128 (4-bit): two groups per pass over the 8-deep ring, no per-iteration tests
+  if (NI4) {                // 4 loads per group: two groups per pass over the 8-deep ring, no per-iteration tests
     const int ngw = total / 4;
+#pragma unroll 1
     for (int gi = 0; gi < ngw; gi += 2) {
       group_start();
 #pragma unroll
@@ -447,7 +450,8 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
   // acc[tile][mt][c]: c0,c1 -> row gq (n0 + 2*tile), cols 2t,2t+1 ; c2,c3 -> row gq+8 (n0 + 2*tile + 1)
   // columns of the tile are owned by cluster ranks in slices of 128/S; every warp writes its partial of a slice
   // into the owner's `red` ([source = 2*rank + khalf][m][128/S]) through distributed shared memory
-  const int slice = 128 / S;
+  // slices are multiples of 4 columns (a lane's float4) and cover the 128-column tile: slice_w = ceil(128/S) -> x4
+  const int slice = p.slice;
   if (S > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (strip_valid) {
     const int owner = n_in_tile / slice;
@@ -461,23 +465,31 @@ __global__ void __launch_bounds__(256, (MT <= 2) ? 2 : 1) woq_gemm_mma_kernel(co
         if (m < p.M) {
           // n0+0: tile0 c(half) ; n0+1: tile0 c(2+half) ; n0+2: tile1 c(half) ; n0+3: tile1 c(2+half)
           const float4 v = make_float4(acc[0][mt][half], acc[0][mt][2 + half], acc[1][mt][half], acc[1][mt][2 + half]);
-          *reinterpret_cast<float4*>(owner_red + ((size_t)src * p.M + m) * slice + (n_in_tile - owner * slice)) = v;
+          *reinterpret_cast<float4*>(owner_red + (src * (int)p.M + m) * slice + (n_in_tile - owner * slice)) = v;
         }
       }
   }
   if (S > 1) cluster.sync(); else __syncthreads();
   {
+    // red: [2S sources][M][slice].  One half-warp per output element: lane l < 2S loads source l, xor-shuffle tree
+    // (fixed order -> deterministic), lane 0 / 16 stores.
     const int nbase = n_tile0 + rank * slice;
-    for (int m = 0; m < (int)p.M; ++m)
-      for (int nl = threadIdx.x; nl < slice; nl += 256) {
-        const int n = nbase + nl;
-        if (n < N) {
-          float sum = 0.f;
-          for (int sp = 0; sp < 2 * S; ++sp) sum += red[((size_t)sp * p.M + m) * slice + nl];
-          if (p.bias) sum += load_as_float(p.bias, p.bias_dtype, n);
-          store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, sum);
-        }
+    const int width = min(slice, 128 - rank * slice);   // the last rank's slice may be shorter
+    const int nsrc = 2 * S;
+    const int hw = lane >> 4, hl = lane & 15;
+    for (int e = warp * 2 + hw; e < (int)p.M * width; e += 16) {
+      const int m = e / width, nl = e - m * width;
+      float v = (hl < nsrc) ? red[(hl * (int)p.M + m) * slice + nl] : 0.f;
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      const int n = nbase + nl;
+      if (hl == 0 && n < N) {
+        if (p.bias) v += load_as_float(p.bias, p.bias_dtype, n);
+        store_from_float(p.y, p.y_dtype, (int64_t)m * N + n, v);
       }
+    }
   }
 }
 
@@ -537,20 +549,24 @@ static bool fast_path_ok(int64_t N, int64_t K, int bits, int g, const int32_t* g
   return (N % 32 == 0) && (g % kstep == 0) && (K % g == 0);
 }
 
-// split-K factor == cluster size (1,2,4,8): enough CTAs for ~2 per SM, at least 2 groups per CTA
+// split-K factor == cluster size in 1..8: as many CTAs as fit in ONE wave of 2 CTAs/SM (a second, nearly empty
+// wave would double the kernel time), at least 2 groups per CTA so both k-halves of a CTA have work
 static int choose_split(int64_t M, int64_t N, int64_t K, int g) {
   const int64_t n_tiles = ceil_div(N, 128);
   const int64_t G = K / g;
-  const int64_t want = 2 * (int64_t)num_sms();
-  int S = 1;
-  while (S < 8 && n_tiles * S < want && G / (2 * S) >= 2) S *= 2;
-  while (S > 1 && G / S < 1) S /= 2;
-  return S;
+  const int64_t slots = 2 * (int64_t)num_sms();
+  int best = 1;
+  for (int S = 1; S <= 8; ++S) {
+    if (G / S < 2 && S > 1) break;
+    if (n_tiles * S <= slots) best = S;
+  }
+  (void)M;
+  return best;
 }
 
 static size_t fast_smem_bytes(int64_t Mc, int mt, int64_t gmax, int g, int bits) {
   const int kpw = 32 / bits;
-  const size_t red = (size_t)2 * Mc * 128 * sizeof(float);
+  const size_t red = (size_t)Mc * kRedPerM * sizeof(float);
   const size_t xs = (size_t)Mc * (gmax * g + 32) * sizeof(__half);
   const size_t xsum = (((size_t)Mc * gmax + 3) & ~(size_t)3) * sizeof(float);
   const size_t sc = (size_t)gmax * 128 * sizeof(__half), zr = (size_t)gmax * (128 / kpw) * sizeof(uint32_t);
@@ -572,9 +588,10 @@ static int launch_fast(GemmParams& p, int64_t Mc, cudaStream_t st) {
   // shrink the split until the tile fits in shared memory
   while (true) {
     p.gmax = (int)ceil_div(p.G, p.S);
-    if (fast_smem_bytes(Mc, mt, p.gmax, p.g, BITS) <= 200 * 1024 || p.S >= 8 || p.G / (p.S * 2) < 1) break;
-    p.S *= 2;
+    if (fast_smem_bytes(Mc, mt, p.gmax, p.g, BITS) <= 200 * 1024 || p.S >= 8 || p.G / (p.S + 1) < 2) break;
+    p.S += 1;
   }
+  p.slice = (int)((ceil_div(128, p.S) + 3) & ~3);
   p.xs_ld = p.gmax * p.g + 32;
   // the k-half exchange buffer aliases xs: make sure the row count covers it
   size_t smem = fast_smem_bytes(Mc, mt, p.gmax, p.g, BITS);
@@ -602,9 +619,10 @@ static int launch_fast(GemmParams& p, int64_t Mc, cudaStream_t st) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
+  const bool ni4 = (p.g == 16 * (32 / BITS));  // 4 sixteen-byte loads per group per lane (g=128 @4-bit, 64 @8-bit)
 #define WOQ_LAUNCH(MT_, POST_)                                                                              \
   do {                                                                                                      \
-    auto kern = woq_gemm_mma_kernel<BITS, MT_, POST_>;                                                      \
+    auto kern = ni4 ? woq_gemm_mma_kernel<BITS, MT_, POST_, true> : woq_gemm_mma_kernel<BITS, MT_, POST_, false>; \
     if (smem > 48 * 1024) WOQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
     WOQ_CUDA(cudaLaunchKernelEx(&cfg, kern, p));                                                            \
     count_launch(1);                                                                                        \
