@@ -257,29 +257,34 @@ def bench_decode(dev, pk):
     for name, N, Kd in LINEARS:
         Wt = (torch.randn(N, Kd, generator=g) * 0.02).to(dev)
         r = ops.rtn_quant_pack(Wt, 4, 128, True)
-        base[name] = (r["qweight"], r["qzeros"], r["scales"])
+        base[name] = (r["qweight"], r["qzeros"], r["scales"], ops.build_stream_layout(r["qweight"], r["qzeros"], r["scales"],
+                                                                                         4, 128, Kd, N))
     for _ in range(LAYERS):
         packs.append({k: tuple(t.clone() for t in v) for k, v in base.items()})
     xh = torch.randn(1, HIDDEN, device=dev, dtype=torch.float16)
     yh = {n: torch.empty(1, N, device=dev, dtype=torch.float16) for n, N, _ in LINEARS}
 
-    def token(flags):
+    def token(flags, use_stream):
         x = xh
         for blk in packs:
             for name, N, Kd in LINEARS:
                 inp = x if Kd == HIDDEN else yh["up"]
-                qw, qz, sc = blk[name]
-                ops.woq_linear(inp, qw, qz, sc, None, 4, 128, Kd, N, out_dtype=torch.float16, flags=flags, out=yh[name])
+                qw, qz, sc, lay = blk[name]
+                if use_stream:
+                    ops.woq_linear_stream(inp, lay, None, 4, 128, Kd, N, out_dtype=torch.float16, flags=flags, out=yh[name])
+                else:
+                    ops.woq_linear(inp, qw, qz, sc, None, 4, 128, Kd, N, out_dtype=torch.float16, flags=flags, out=yh[name])
             x = yh["down"]
 
     res = {}
     by = sum(N * Kd // 2 + 2 * N * Kd // 128 + N * Kd // 256 + 2 * Kd + 2 * N for _, N, Kd in LINEARS) * LAYERS
-    for flags, tag in ((0, "plain"), (2, "pdl")):
-        token(flags)
+    for flags, use_stream, tag in ((0, False, "optimum_layout"), (2, False, "optimum_layout_pdl"),
+                                   (0, True, "stream_layout"), (2, True, "stream_layout_pdl")):
+        token(flags, use_stream)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            token(flags)
+            token(flags, use_stream)
         for _ in range(3):
             graph.replay()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,7 +300,7 @@ def bench_decode(dev, pk):
     return dict(decode=dict(metric="Llama-2-7B INT4 decode tokens/s (224 WOQ linears, batch 1, CUDA graph)", **best,
                             variants=res, bytes_per_token=by, dequant_gemm_tflops=round(
                                 2 * sum(N * Kd for _, N, Kd in LINEARS) * LAYERS / (best["ms_per_token"] * 1e9), 2)),
-                roofline_decode=dict(bound="hbm", kernel="woq_gemm_mma_kernel<4,1,true>", achieved=best["GBs"],
+                roofline_decode=dict(bound="hbm", kernel="woq_gemm_stream_kernel / woq_gemm_mma_kernel (best variant)", achieved=best["GBs"],
                                      peak=pk["hbm_gbs"], unit="GB/s", frac=round(best["GBs"] / pk["hbm_gbs"], 4),
                                      traffic=None, peak_source=pk["source"]))
 

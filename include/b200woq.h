@@ -115,6 +115,19 @@ int b200woq_linear_forward(const void* x, int x_dtype, int64_t M, int64_t K, int
                            const float* input_scale, void* y, int y_dtype, int bits, int group_size,
                            void* workspace, int64_t workspace_bytes, int flags, void* stream);
 
+/* Small-batch (M <= 16) 4-bit path on a derived, B200-native "stream layout" (woq_stream.cu): one contiguous
+ * record per (128-column tile, group) = lane-ordered packed words + scales + decoded zero-points, streamed by TMA
+ * bulk copies.  Built once per module from the optimum-format tensors (the reference likewise caches a derived
+ * weight at first forward, modules.py:603-604).  b200woq_stream_layout_bytes returns 0 when the shape is not
+ * eligible (bits != 4, group % 32, N % 32). */
+int64_t b200woq_stream_layout_bytes(int64_t N, int64_t K, int bits, int group_size);
+int b200woq_build_stream_layout(const int32_t* qweight, const int32_t* qzeros, const void* scales16, int64_t N,
+                                int64_t K, int bits, int group_size, void* out, void* stream);
+int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N,
+                                  const void* stream_layout, const void* bias, int bias_dtype,
+                                  const float* input_scale, void* y, int y_dtype, int bits, int group_size,
+                                  int flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K1-K3  GPTQ calibration (gptq.py:1089-1351)
  * ---------------------------------------------------------------------------------------------- */

@@ -35,6 +35,11 @@ _SIGS = {
     "b200woq_linear_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                        c_void_p, c_int64, c_int, c_void_p]),
+    "b200woq_stream_layout_bytes": (c_int64, [c_int64, c_int64, c_int, c_int]),
+    "b200woq_build_stream_layout": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
+                                            c_void_p]),
+    "b200woq_linear_forward_stream": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int,
+                                              c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200woq_hessian_accumulate": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "b200woq_hessian_finalize": (c_int, [c_void_p, c_int64, c_double, c_float, c_void_p, c_void_p, c_void_p]),
     "b200woq_gptq_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),

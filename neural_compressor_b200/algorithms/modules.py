@@ -13,6 +13,7 @@ consume it unchanged; pack / unpack / recover / forward are sm_100a kernels behi
 from __future__ import annotations
 
 import math
+import os
 from abc import abstractmethod
 
 import torch
@@ -123,8 +124,24 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
         return ops.dequantize(self.qweight, self.qzeros, self.scales, self.bits, self.group_size, self.in_features,
                               self.out_features, self.g_idx)
 
+    def _stream_layout(self):
+        """Lazily derived copy of the packed tensors in the B200 stream layout (not part of the state_dict)."""
+        key = (self.qweight.data_ptr(), self.qzeros.data_ptr(), self.scales.data_ptr())
+        if getattr(self, "_stream_key", None) != key:
+            self._stream = ops.build_stream_layout(self.qweight, self.qzeros, self.scales, self.bits, self.group_size,
+                                                   self.in_features, self.out_features)
+            self._stream_key = key
+        return self._stream
+
     def forward(self, input, input_scale=None):
         out_dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16) else torch.float32
+        rows = input.numel() // self.in_features
+        if (rows <= 16 and self.bits == 4 and self.g_idx is None and self.qweight.is_cuda
+                and os.environ.get("B200WOQ_STREAM", "1") != "0"):
+            layout = self._stream_layout()
+            if layout is not None:
+                return ops.woq_linear_stream(input, layout, self.bias, self.bits, self.group_size, self.in_features,
+                                             self.out_features, input_scale=input_scale, out_dtype=out_dtype)
         return ops.woq_linear(input, self.qweight, self.qzeros, self.scales, self.bias, self.bits, self.group_size,
                               self.in_features, self.out_features, g_idx=self.g_idx, input_scale=input_scale,
                               out_dtype=out_dtype)

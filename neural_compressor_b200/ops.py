@@ -144,6 +144,37 @@ def woq_linear(x, qweight, qzeros, scales, bias, bits, group_size, in_features, 
     return out.reshape(*lead, out_features)
 
 
+def build_stream_layout(qweight, qzeros, scales, bits, group_size, in_features, out_features):
+    """Derived B200-native layout for the small-batch 4-bit path (woq_stream.cu); None when not eligible."""
+    require_cuda(qweight, "qweight")
+    lib = _lib.load()
+    nbytes = lib.b200woq_stream_layout_bytes(out_features, in_features, bits, group_size)
+    if nbytes <= 0:
+        return None
+    out = torch.empty(nbytes, dtype=torch.uint8, device=qweight.device)
+    check(lib.b200woq_build_stream_layout(ptr(qweight), ptr(qzeros), ptr(scales), out_features, in_features, bits,
+                                          group_size, ptr(out), stream_ptr(qweight.device)), "build_stream_layout")
+    return out
+
+
+def woq_linear_stream(x, stream_layout, bias, bits, group_size, in_features, out_features, input_scale=None,
+                      out_dtype=torch.float32, flags=0, out=None):
+    """INCWeightOnlyLinear.forward for M <= 16 on the stream layout (TMA bulk-copy ring)."""
+    require_cuda(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, in_features)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((M, out_features), dtype=out_dtype, device=x.device)
+    check(_lib.load().b200woq_linear_forward_stream(ptr(x2), dt(x2), M, in_features, out_features, ptr(stream_layout),
+                                                    ptr(bias), dt(bias) if bias is not None else 0, ptr(input_scale),
+                                                    ptr(out), dt(out), bits, group_size, flags, stream_ptr(x.device)),
+          "linear_forward_stream")
+    return out.reshape(*lead, out_features)
+
+
 # ------------------------------------------------------------------ K1-K3: GPTQ
 PROFILE_HOOK = None  # bench.py sets this to a list: (start_event, end_event, algorithmic_flops) per Hessian launch
 

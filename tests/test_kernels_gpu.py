@@ -114,6 +114,36 @@ def test_woq_linear_fast_path_vs_oracle(ops, bits, sym, N, K, g):
     assert y.dtype == torch.float16 and _rel(y.float().cpu(), ref) < 3e-3
 
 
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("N,K,g", [(256, 512, 128), (96, 384, 32), (4096, 4096, 128), (1024, 2752, 64), (11008, 1024, 128)])
+def test_woq_linear_stream_layout_vs_oracle(ops, sym, N, K, g):
+    """Small-batch TMA-streamed path on the derived stream layout (woq_stream.cu)."""
+    gen = torch.Generator().manual_seed(N + K + g)
+    W = torch.randn(N, K, generator=gen) * 0.02
+    q, s, z = O.rtn_quantize(W, 4, g, "sym" if sym else "asym")
+    qw, qz, sc = O.pack_optimum(q, s, z, 4, g)
+    bias = (torch.randn(N, generator=gen) * 0.1).half()
+    w_ref = O.recover_fp16(qw, qz, sc, 4, g, K, N).float()
+    layout = ops.build_stream_layout(qw.to(DEV), qz.to(DEV), sc.to(DEV), 4, g, K, N)
+    assert layout is not None
+    for M in (1, 2, 5, 8, 13, 16):
+        x = torch.randn(M, K, generator=gen)
+        ref = torch.nn.functional.linear(x, w_ref, bias.float())
+        for xdt in (torch.float16, torch.float32, torch.bfloat16):
+            for flags in (0, 2):
+                y = ops.woq_linear_stream(x.to(xdt).to(DEV), layout, bias.to(DEV), 4, g, K, N, flags=flags)
+                ref_x = torch.nn.functional.linear(x.to(xdt).float(), w_ref, bias.float())
+                assert _rel(y.cpu(), ref_x) < 2e-3, (sym, N, K, g, M, xdt, flags, _rel(y.cpu(), ref_x))
+        y2 = ops.woq_linear_stream(x.half().to(DEV), layout, bias.to(DEV), 4, g, K, N)
+        y3 = ops.woq_linear_stream(x.half().to(DEV), layout, bias.to(DEV), 4, g, K, N)
+        assert torch.equal(y2, y3)  # deterministic split-K reduction
+    x = torch.randn(3, K, generator=gen)
+    isc = torch.rand(K, generator=gen) + 0.5
+    ref = torch.nn.functional.linear(x * isc, w_ref, bias.float())
+    y = ops.woq_linear_stream(x.to(DEV), layout, bias.to(DEV), 4, g, K, N, input_scale=isc.to(DEV), out_dtype=torch.float16)
+    assert y.dtype == torch.float16 and _rel(y.float().cpu(), ref) < 3e-3
+
+
 def test_woq_linear_g_idx_general_path(ops):
     gen = torch.Generator().manual_seed(5)
     N, K, g, bits = 64, 256, 32, 4

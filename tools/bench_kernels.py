@@ -46,6 +46,25 @@ def bench_gemv(out):
     for name, N, K in shapes:
         copies = max(4, int(math.ceil(400e6 / (N * K / 2))))  # rotate over > L2-size worth of weights
         packs = [make_packed(N, K, seed=i) for i in range(copies)]
+        layouts = [ops.build_stream_layout(qw, qz, sc, 4, 128, K, N) for (qw, qz, sc) in packs]
+        for M in (1, 8, 16):
+            x = torch.randn(M, K, device=DEV, dtype=torch.float16)
+            y = torch.empty(M, N, device=DEV, dtype=torch.float16)
+            for flags in (0, 2):
+                def run_s():
+                    for lay in layouts:
+                        ops.woq_linear_stream(x, lay, None, 4, 128, K, N, out_dtype=torch.float16, flags=flags, out=y)
+                run_s()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run_s()
+                ms = time_cuda(g.replay, iters=20) / copies
+                by = gemv_bytes(M, N, K)
+                res.append(dict(shape=name, M=M, pdl=bool(flags & 2), impl="stream", us=ms * 1e3, GBs=by / ms / 1e6,
+                                frac_hbm=by / ms / 1e6 / PEAK["hbm_gbs"], tflops=2 * M * N * K / ms / 1e9))
+                print(res[-1], file=sys.stderr)
+        del layouts
         for M in (1, 4, 8, 16, 32, 64):
             x = torch.randn(M, K, device=DEV, dtype=torch.float16)
             y = torch.empty(M, N, device=DEV, dtype=torch.float16)
