@@ -136,7 +136,7 @@ def run_b200(args):
     lib = _lib.load()
     pk = peaks()
     W, K = args.warmup, args.steps
-    n_blocks_needed = min(LAYERS, 2 * (W + K)) if args.e2e else min(LAYERS, W + K)
+    n_blocks_needed = min(LAYERS, (2 * (W + K) if args.e2e else (W + K)) + (1 if args.phases else 0))
     log(f"building Llama-2-7B-shape model with {n_blocks_needed} of {LAYERS} blocks on {dev}")
     model = build_llama(dev, n_blocks_needed)
     log("model built")
@@ -214,6 +214,18 @@ def run_b200(args):
                         algorithmic="T*C*(C+128) flops per launch: the symmetric half of the reference's 2*T*C^2")
     ops.PROFILE_HOOK = None
 
+    phases = None
+    if args.phases and W + K < n_blocks_needed:
+        engine.profile = True
+        for k_ in engine.timing:
+            engine.timing[k_] = 0.0
+        with torch.no_grad():
+            engine.quantize_block(W + K)
+        engine.profile = False
+        phases = {k_: round(v_ * 1e3, 1) for k_, v_ in engine.timing.items()}
+        log(f"phase breakdown of one extra block (ms, with syncs): {phases}")
+        W += 1  # that block is consumed
+
     e2e = None
     if args.e2e and W + K + K <= n_blocks_needed:
         blk_bytes = sum(p_.numel() * p_.element_size() for p_ in engine.blocks_info["transformers"][W + K].parameters())
@@ -231,7 +243,7 @@ def run_b200(args):
                                     "128 synthetic calib seqs x 2048 tokens; step = one decoder block of the 32",
                            global_batch=N_SAMPLES, seq_len=SEQ, parallelism=f"calib-dp{world}",
                            l2="inputs >> L2 (2.1 GB activations, 0.4 GB weights per step)"),
-               gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline)
+               gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline, phases_ms=phases)
     if rank == 0 and args.decode:
         del model, engine
         torch.cuda.empty_cache()
@@ -377,6 +389,7 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
+    ap.add_argument("--phases", action="store_true", help="also report a per-phase breakdown of one extra block")
     ap.add_argument("--no-decode", dest="decode", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     a = ap.parse_args()

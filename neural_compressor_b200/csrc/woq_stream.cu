@@ -17,6 +17,8 @@
 // when x is staged, which removes the shifts: 5 integer ops per 8 codes.
 #include <cooperative_groups.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace b200woq {
@@ -212,13 +214,20 @@ __global__ void __launch_bounds__(160, 3) woq_gemm_stream_kernel(const Params p)
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
 
-    float acc[2][MT][4], accg[2][MT][4];
+    // NSET independent per-group accumulator sets: the legacy HMMA has a long dependent-issue latency on sm_100, so
+    // consecutive MMAs never target the same accumulator (step A / step B x iteration parity); summed at group end
+    constexpr int NSET = (MT == 1) ? 4 : 2;
+    float acc[2][MT][4], accg[NSET][2][MT][4];
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < MT; ++b)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[a][b][c] = accg[a][b][c] = 0.f;
+        for (int c = 0; c < 4; ++c) {
+          acc[a][b][c] = 0.f;
+#pragma unroll
+          for (int q = 0; q < NSET; ++q) accg[q][a][b][c] = 0.f;
+        }
 
     const int NI = p.NI;
     int xoff = t * 8;
@@ -233,8 +242,8 @@ __global__ void __launch_bounds__(160, 3) woq_gemm_stream_kernel(const Params p)
         const float sf[4] = {__low2float(s01), __high2float(s01), __low2float(s23), __high2float(s23)};
         const float zf[4] = {(float)(zq & 0xffu), (float)((zq >> 8) & 0xffu), (float)((zq >> 16) & 0xffu), (float)(zq >> 24)};
         const uint4* wsrc = reinterpret_cast<const uint4*>(rec + strip * NI * 512) + lane;
-#pragma unroll 4
-        for (int it = 0; it < NI; ++it) {
+        auto do_it = [&](int it, auto sa_tag) {
+          constexpr int sa = decltype(sa_tag)::value, sb = sa + 1;
           const uint4 wv = wsrc[it * 32];
           const uint32_t wr[4] = {wv.x, wv.y, wv.z, wv.w};
           uint32_t P[4][4];
@@ -254,12 +263,17 @@ __global__ void __launch_bounds__(160, 3) woq_gemm_stream_kernel(const Params p)
               const uint4 v = *reinterpret_cast<const uint4*>(xs + m * p.xs_ld + xoff);
               xb[0] = v.x; xb[1] = v.y; xb[2] = v.z; xb[3] = v.w;
             }
-            mma_16816(accg[0][mt], P[0][0], P[1][0], P[0][1], P[1][1], xb[0], xb[1]);
-            mma_16816(accg[1][mt], P[2][0], P[3][0], P[2][1], P[3][1], xb[0], xb[1]);
-            mma_16816(accg[0][mt], P[0][2], P[1][2], P[0][3], P[1][3], xb[2], xb[3]);
-            mma_16816(accg[1][mt], P[2][2], P[3][2], P[2][3], P[3][3], xb[2], xb[3]);
+            mma_16816(accg[sa][0][mt], P[0][0], P[1][0], P[0][1], P[1][1], xb[0], xb[1]);
+            mma_16816(accg[sa][1][mt], P[2][0], P[3][0], P[2][1], P[3][1], xb[0], xb[1]);
+            mma_16816(accg[sb][0][mt], P[0][2], P[1][2], P[0][3], P[1][3], xb[2], xb[3]);
+            mma_16816(accg[sb][1][mt], P[2][2], P[3][2], P[2][3], P[3][3], xb[2], xb[3]);
           }
           xoff += 32;
+        };
+#pragma unroll 2
+        for (int it = 0; it < NI; it += 2) {
+          do_it(it, std::integral_constant<int, 0>{});
+          if (it + 1 < NI) do_it(it + 1, std::integral_constant<int, (NSET == 4) ? 2 : 0>{});
         }
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
@@ -269,11 +283,19 @@ __global__ void __launch_bounds__(160, 3) woq_gemm_stream_kernel(const Params p)
 #pragma unroll
           for (int tile = 0; tile < 2; ++tile) {
             const float sa = sf[2 * tile], sb = sf[2 * tile + 1], za = zf[2 * tile], zb = zf[2 * tile + 1];
-            acc[tile][mt][0] = fmaf(fmaf(accg[tile][mt][0], 16777216.f, -za * x0), sa, acc[tile][mt][0]);
-            acc[tile][mt][1] = fmaf(fmaf(accg[tile][mt][1], 16777216.f, -za * x1), sa, acc[tile][mt][1]);
-            acc[tile][mt][2] = fmaf(fmaf(accg[tile][mt][2], 16777216.f, -zb * x0), sb, acc[tile][mt][2]);
-            acc[tile][mt][3] = fmaf(fmaf(accg[tile][mt][3], 16777216.f, -zb * x1), sb, acc[tile][mt][3]);
-            accg[tile][mt][0] = accg[tile][mt][1] = accg[tile][mt][2] = accg[tile][mt][3] = 0.f;
+            float gsum[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              gsum[c] = accg[0][tile][mt][c];
+#pragma unroll
+              for (int q = 1; q < NSET; ++q) gsum[c] += accg[q][tile][mt][c];
+#pragma unroll
+              for (int q = 0; q < NSET; ++q) accg[q][tile][mt][c] = 0.f;
+            }
+            acc[tile][mt][0] = fmaf(fmaf(gsum[0], 16777216.f, -za * x0), sa, acc[tile][mt][0]);
+            acc[tile][mt][1] = fmaf(fmaf(gsum[1], 16777216.f, -za * x1), sa, acc[tile][mt][1]);
+            acc[tile][mt][2] = fmaf(fmaf(gsum[2], 16777216.f, -zb * x0), sb, acc[tile][mt][2]);
+            acc[tile][mt][3] = fmaf(fmaf(gsum[3], 16777216.f, -zb * x1), sb, acc[tile][mt][3]);
           }
         }
       } else {

@@ -222,7 +222,9 @@ def cholesky_inverse_upper(H: torch.Tensor) -> torch.Tensor:
         L = torch.linalg.cholesky(H)
         Hi = torch.cholesky_inverse(L)
         return torch.linalg.cholesky(Hi, upper=True).contiguous()
-    Lf = torch.linalg.cholesky(H.flip(0, 1))
+    # cholesky_ex(check_errors=False): no device->host sync on the factorisation status (a failed factorisation
+    # yields NaNs that surface in the codes; the damped Hessian is positive definite by construction)
+    Lf = torch.linalg.cholesky_ex(H.flip(0, 1), check_errors=False).L
     Ut = Lf.flip(0, 1)  # upper triangular, H = Ut Ut^T
     eye = torch.eye(H.shape[0], dtype=H.dtype, device=H.device)
     return torch.linalg.solve_triangular(Ut, eye, upper=True).contiguous()
