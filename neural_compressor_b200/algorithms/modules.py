@@ -21,6 +21,11 @@ import torch
 from .. import ops
 
 
+# Batches up to this many rows take the per-warp TMA-ring kernel on the derived stream layout (woq_stream.cu); larger
+# batches amortise the weight read over more rows and use the cluster split-K kernel on the optimum tensors.
+STREAM_MAX_ROWS = int(os.environ.get("B200WOQ_STREAM_MAX_ROWS", "4"))
+
+
 class WeightOnlyLinear(torch.nn.Module):
     """modules.py:91-154."""
 
@@ -136,7 +141,7 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
     def forward(self, input, input_scale=None):
         out_dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16) else torch.float32
         rows = input.numel() // self.in_features
-        if (rows <= 16 and self.bits == 4 and self.g_idx is None and self.qweight.is_cuda
+        if (rows <= STREAM_MAX_ROWS and self.bits == 4 and self.g_idx is None and self.qweight.is_cuda
                 and os.environ.get("B200WOQ_STREAM", "1") != "0"):
             layout = self._stream_layout()
             if layout is not None:

@@ -159,7 +159,7 @@ def build_stream_layout(qweight, qzeros, scales, bits, group_size, in_features, 
 
 def woq_linear_stream(x, stream_layout, bias, bits, group_size, in_features, out_features, input_scale=None,
                       out_dtype=torch.float32, flags=0, out=None):
-    """INCWeightOnlyLinear.forward for M <= 16 on the stream layout (TMA bulk-copy ring)."""
+    """INCWeightOnlyLinear.forward for M <= 4 on the stream layout (per-warp TMA bulk-copy rings)."""
     require_cuda(x, "x")
     lead = x.shape[:-1]
     x2 = x.reshape(-1, in_features)

@@ -40,17 +40,25 @@ def gemv_bytes(M, N, K, g=128, bits=4, xb=2, yb=2):
     return N * K * bits // 8 + 2 * N * K // g + N * K // (2 * g) * bits // 4 + xb * M * K + yb * M * N
 
 
-def bench_gemv(out):
+def bench_gemvs(out):
+    bench_gemv(out, stream_only=True)
+
+
+def bench_gemv(out, stream_only=False):
     shapes = [("qkv/o 4096x4096", 4096, 4096), ("gate/up 11008x4096", 11008, 4096), ("down 4096x11008", 4096, 11008)]
+    import os
+    if os.environ.get("B200WOQ_BENCH_SHAPES"):  # e.g. "4096x128,22016x4096" (NxK)
+        shapes = [(f"custom/{t}", int(t.split("x")[0]), int(t.split("x")[1]))
+                  for t in os.environ["B200WOQ_BENCH_SHAPES"].split(",")]
     res = []
     for name, N, K in shapes:
-        copies = max(4, int(math.ceil(400e6 / (N * K / 2))))  # rotate over > L2-size worth of weights
+        copies = min(64, max(4, int(math.ceil(400e6 / (N * K / 2)))))  # rotate over > L2-size worth of weights
         packs = [make_packed(N, K, seed=i) for i in range(copies)]
         layouts = [ops.build_stream_layout(qw, qz, sc, 4, 128, K, N) for (qw, qz, sc) in packs]
-        for M in (1, 8, 16):
+        for M in (1, 2, 4):
             x = torch.randn(M, K, device=DEV, dtype=torch.float16)
             y = torch.empty(M, N, device=DEV, dtype=torch.float16)
-            for flags in (0, 2):
+            for flags in ((2,) if stream_only else (0, 2)):
                 def run_s():
                     for lay in layouts:
                         ops.woq_linear_stream(x, lay, None, 4, 128, K, N, out_dtype=torch.float16, flags=flags, out=y)
@@ -65,7 +73,9 @@ def bench_gemv(out):
                                 frac_hbm=by / ms / 1e6 / PEAK["hbm_gbs"], tflops=2 * M * N * K / ms / 1e9))
                 print(res[-1], file=sys.stderr)
         del layouts
-        for M in (1, 4, 8, 16, 32, 64):
+        if stream_only:
+            continue
+        for M in (1, 2, 4, 8, 16, 32, 64):
             x = torch.randn(M, K, device=DEV, dtype=torch.float16)
             y = torch.empty(M, N, device=DEV, dtype=torch.float16)
             for flags in (0, 2):
