@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import math
 import os
+import contextlib
 import time
 from functools import partial
 from typing import Dict, List
@@ -114,6 +115,12 @@ class _HessianBank:
         n = torch.tensor([float(self.nsamples)], device=self.acc[0].device if self.acc else "cpu")
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
         self.nsamples = int(round(n.item()))
+
+
+def _dist_world():
+    import torch.distributed as dist
+
+    return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
 
 
 class RAWGPTQuantizer:
@@ -321,6 +328,12 @@ class RAWGPTQuantizer:
         return self.model
 
     @torch.no_grad()
+    def _side_streams(self, n):
+        pool = getattr(self, "_streams", None)
+        if pool is None or len(pool) != n:
+            pool = self._streams = [torch.cuda.Stream(device=self.device) for _ in range(n)]
+        return pool
+
     def quantize_block(self, block_idx: int):
         blocks = self.blocks_info["transformers"]
         self.rechunk_calibration()
@@ -349,9 +362,21 @@ class RAWGPTQuantizer:
             bank.all_reduce()
             t0 = self._sync_time("hessian_fwd", t0)
             # ---- Hessian -> inverse factor, once per distinct input (gptq.py:1189-1231) ----
+            # The distinct Hessians of a block (4 for Llama) and then its layers (7) are independent given the
+            # Hessians: the Cholesky chains (latency-bound panel factorisations) and the column loops (N/4 warps each,
+            # far from filling 148 SMs) are issued round-robin on side streams and joined before forward #2.
             results = {}
             by_slot: Dict[tuple, tuple] = {}
             keys_of_slot: Dict[int, set] = {}
+            main = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+            n_side = 1 if (self.profile or main is None) else max(1, int(os.environ.get("B200WOQ_GPTQ_STREAMS", "4")))
+            side = self._side_streams(n_side) if n_side > 1 else []
+            for st in side:
+                st.wait_stream(main)
+
+            def on(idx):
+                return torch.cuda.stream(side[idx % len(side)]) if side else contextlib.nullcontext()
+
             for lname in layers:
                 cfg = self.get_layer_config(self.full_name(lname, block_idx))
                 keys_of_slot.setdefault(bank.layer_to_slot[lname], set()).add(
@@ -362,7 +387,9 @@ class RAWGPTQuantizer:
                     raise NotImplementedError("static_groups / hybrid_order / fp8_aware / double quant: SURVEY §8 f3")
                 slot = bank.layer_to_slot[lname]
                 key = (slot, float(cfg["percdamp"]), bool(cfg["act_order"]))
-                if key not in by_slot:
+                if key in by_slot:
+                    continue
+                with on(len(by_slot)):
                     # finalize is in place: clone only when several configs share one raw accumulator
                     Hc = bank.acc[slot].clone() if len(keys_of_slot[slot]) > 1 else bank.acc[slot]
                     Hc, dead = ops.hessian_finalize(Hc, bank.nsamples, cfg["percdamp"])
@@ -374,25 +401,41 @@ class RAWGPTQuantizer:
                     t1 = time.perf_counter()
                     Hinv = ops.cholesky_inverse_upper(Hc)
                     self._sync_time("cholesky", t1)
-                    by_slot[key] = (Hinv, dead, perm)
-                Hinv, dead, perm = by_slot[key]
+                    done = torch.cuda.Event() if side else None
+                    if done is not None:
+                        done.record()
+                by_slot[key] = (Hinv, dead, perm, done)
+            # the row-sharded path issues NCCL collectives: keep those on one stream so every rank orders them alike
+            fq_side = side if _dist_world() == 1 else []
+            if side and not fq_side:
+                for st in side:
+                    main.wait_stream(st)
+            for li, (lname, layer) in enumerate(layers.items()):
+                cfg = self.get_layer_config(self.full_name(lname, block_idx))
+                key = (bank.layer_to_slot[lname], float(cfg["percdamp"]), bool(cfg["act_order"]))
+                Hinv, dead, perm, done = by_slot[key]
                 # ---- fasterquant (gptq.py:704-713) ----
                 t1 = time.perf_counter()
-                W = layer.weight.data
-                W = (W.t() if _is_conv1d(layer) else W).float()
-                W = (W[:, perm] if perm is not None else W).contiguous().clone()
-                r = self._fasterquant_rows_sharded(W, Hinv, dead, cfg)
-                if perm is not None:
-                    inv = torch.argsort(perm)
-                    r["Q"] = r["Q"][:, inv].contiguous()
-                    r["codes"] = r["codes"][:, inv].contiguous()
-                    r["perm"] = perm
-                Q = r.pop("Q")
-                layer.weight.data = (Q.t().contiguous() if _is_conv1d(layer) else Q).to(layer.weight.dtype)
+                with (torch.cuda.stream(fq_side[li % len(fq_side)]) if fq_side else contextlib.nullcontext()):
+                    if fq_side and done is not None:
+                        torch.cuda.current_stream(self.device).wait_event(done)
+                    W = layer.weight.data
+                    W = (W.t() if _is_conv1d(layer) else W).float()
+                    W = (W[:, perm] if perm is not None else W).contiguous().clone()
+                    r = self._fasterquant_rows_sharded(W, Hinv, dead, cfg)
+                    if perm is not None:
+                        inv = torch.argsort(perm)
+                        r["Q"] = r["Q"][:, inv].contiguous()
+                        r["codes"] = r["codes"][:, inv].contiguous()
+                        r["perm"] = perm
+                    Q = r.pop("Q")
+                    layer.weight.data = (Q.t().contiguous() if _is_conv1d(layer) else Q).to(layer.weight.dtype)
                 results[lname] = r
                 logger.info(f"block {block_idx} {lname}: error {r['losses'].sum().item():.6f}" if self.profile else
                             f"block {block_idx} {lname} quantized")
                 self._sync_time("fasterquant", t1)
+            for st in fq_side:
+                main.wait_stream(st)
             del bank, by_slot
             # ---- forward pass #2: propagate quantised outputs (gptq.py:749-762) ----
             t0 = time.perf_counter()

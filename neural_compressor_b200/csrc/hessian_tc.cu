@@ -23,6 +23,8 @@
 #include <mutex>
 
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace b200woq {
 
@@ -35,6 +37,7 @@ constexpr int B_BYTES = (TN / 64) * BOX_BYTES; // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NUM_EPI_THREADS = 128;
+constexpr int kSuperRowsDefault = 16;  // row tiles per rasterisation super-row
 constexpr int TMEM_COLS = 512;      // two 128x256 fp32 accumulators
 constexpr int SEG_KB = 32;          // k-blocks (of BK tokens) per accumulation segment = 2048 tokens
 
@@ -95,11 +98,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// grid = (ceil(C/256), ceil(C/128)); block = 192 threads
+// grid = one CTA per (128 x 256) tile of the super-row enumeration below; block = 192 threads
 __global__ void __launch_bounds__(192, 1)
     hessian_syrk_tc_kernel(const __grid_constant__ CUtensorMap tmap, int64_t Ttok, int64_t C, float* __restrict__ H,
-                           uint32_t idesc) {
-  const int tj = blockIdx.x, ti = blockIdx.y;
+                           uint32_t idesc, int super_rows) {
+  // Rasterisation: tiles are enumerated in super-rows of `super_rows` row tiles, column tile by column tile, so the
+  // ~148 CTAs in flight cover a 16 x 9 patch of tiles.  They sweep the token axis roughly in step, so what a wave pulls
+  // from HBM is (16*128 + 9*256) channels x T instead of (4*128 + all) channels x T with a row-major order: at
+  // C = 11008 (X = 360 MB, 3x the L2) that is 2.5x less DRAM traffic.
+  int id = blockIdx.x, ti0 = 0, rows, tjmin;
+  const int ny = (int)((C + TM - 1) / TM), nx = (int)((C + TN - 1) / TN);
+  for (;;) {
+    rows = min(super_rows, ny - ti0);
+    tjmin = ti0 >> 1;  // tile (ti, tj) touches the upper triangle iff ti <= 2*tj + 1
+    const int cnt = rows * (nx - tjmin);
+    if (id < cnt) break;
+    id -= cnt;
+    ti0 += super_rows;
+  }
+  const int tj = tjmin + id / rows, ti = ti0 + id % rows;
   if (ti > 2 * tj + 1) return;  // below the block diagonal: mirrored later
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -270,8 +287,12 @@ int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C,
     WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((unsigned)ceil_div(C, TN), (unsigned)ceil_div(C, TM));
-  hessian_syrk_tc_kernel<<<grid, 192, SMEM_BYTES, st>>>(tmap, T, C, Hsum, idesc);
+  static const int super_rows =
+      getenv("B200WOQ_SYRK_SUPER_ROWS") ? std::max(1, atoi(getenv("B200WOQ_SYRK_SUPER_ROWS"))) : kSuperRowsDefault;
+  const int ny = (int)ceil_div(C, TM), nx = (int)ceil_div(C, TN);
+  unsigned total = 0;
+  for (int ti0 = 0; ti0 < ny; ti0 += super_rows) total += (unsigned)(std::min(super_rows, ny - ti0) * (nx - (ti0 >> 1)));
+  hessian_syrk_tc_kernel<<<total, 192, SMEM_BYTES, st>>>(tmap, T, C, Hsum, idesc, super_rows);
   WOQ_LAUNCH_CHECK();
   return 0;
 }
