@@ -173,9 +173,11 @@ def run_b200(args):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.b200woq_launch_count()
         s.record()
+        torch.cuda.nvtx.range_push("timed_steps")  # lets `ncu --nvtx --nvtx-include "timed_steps/"` list exactly these
         with torch.no_grad():
             for b in range(first, first + count):
                 engine.quantize_block(b)
+        torch.cuda.nvtx.range_pop()
         e.record()
         barrier()
         ms = s.elapsed_time(e)

@@ -22,7 +22,8 @@
 namespace b200woq {
 
 constexpr int SUB = 128;  // columns per register-resident sub-block
-constexpr int RW = 4;     // rows per warp: 4 independent dependency chains interleave in one warp
+constexpr int RW = 2;     // rows per warp: independent dependency chains interleaved in one warp
+constexpr int SUB_WARPS = 8;  // warps per CTA of the column-loop kernel
 
 // Correctly rounded fp32 division by a divisor that is reused many times (Markstein 1990): with r = RN(1/d),
 // q0 = RN(a*r), rem = a - q0*d (exact in one FMA), RN(q0 + rem*r) == RN(a/d) unless d's significand is all ones
@@ -121,22 +122,40 @@ __global__ void zero_dead_columns_kernel(float* __restrict__ W, int64_t N, int64
 }
 
 // column loop over one sub-block [c0, c0+ncols), ncols <= 128.
-// CTA = 4 warps x RW rows.  Per-column constants (d = Hinv[i,i], RN(1/d), 0.5/d^2, "needs IEEE division" flag) are
+// CTA = SUB_WARPS warps x RW rows.  Per-column constants (d = Hinv[i,i], RN(1/d), 0.5/d^2, "needs IEEE division" flag) are
 // computed once per CTA into shared memory, so the serial loop body is ~30 instructions per (column, row).
 // Err is written TRANSPOSED (ErrT[col_in_block][row]) so the lazy-update GEMM reads it coalesced.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(32 * SUB_WARPS)
     gptq_subblock_kernel(float* __restrict__ W, const float* __restrict__ Hinv, int64_t N, int64_t C, int64_t c0,
                          int ncols, int g, int64_t G, float maxq, const float* __restrict__ scale,
                          const float* __restrict__ zero, uint8_t* __restrict__ codes, float* __restrict__ Q,
                          float* __restrict__ ErrT, int64_t err_col0, float* __restrict__ losses) {
-  extern __shared__ float hs[];  // [ncols][SUB+1] upper-triangular diagonal block of Hinv, then 4 x [SUB] column constants
-  float* dcol = hs + SUB * (SUB + 1);
+  extern __shared__ __align__(16) float hs[];  // [ncols][SUB] upper-triangular diagonal block of Hinv, then 4 x [SUB] column constants
+  float* dcol = hs + SUB * SUB;
   float* rcol = dcol + SUB;
   float* lcol = rcol + SUB;
   uint32_t* fcol = reinterpret_cast<uint32_t*>(lcol + SUB);
-  for (int e = threadIdx.x; e < ncols * SUB; e += blockDim.x) {
-    const int r = e / SUB, c = e % SUB;
-    hs[r * (SUB + 1) + c] = (c < ncols && c >= r) ? Hinv[(c0 + r) * C + c0 + c] : 0.f;
+  {  // a warp per row of the diagonal block, 4 consecutive columns per lane (one 16-byte load when aligned)
+    const int lane_ = threadIdx.x & 31, c = lane_ * 4;
+    const bool vec_ok = ((C & 3) == 0) && ((c0 & 3) == 0);
+#pragma unroll 4
+    for (int r = threadIdx.x >> 5; r < ncols; r += SUB_WARPS) {
+      const float* src = Hinv + (c0 + r) * C + c0 + c;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (vec_ok && c + 3 < ncols) {
+        v = *reinterpret_cast<const float4*>(src);
+      } else {
+        if (c + 0 < ncols) v.x = src[0];
+        if (c + 1 < ncols) v.y = src[1];
+        if (c + 2 < ncols) v.z = src[2];
+        if (c + 3 < ncols) v.w = src[3];
+      }
+      if (c + 0 < r) v.x = 0.f;
+      if (c + 1 < r) v.y = 0.f;
+      if (c + 2 < r) v.z = 0.f;
+      if (c + 3 < r) v.w = 0.f;
+      *reinterpret_cast<float4*>(hs + r * SUB + c) = v;
+    }
   }
   for (int i = threadIdx.x; i < ncols; i += blockDim.x) {
     const float d = Hinv[(c0 + i) * C + c0 + i];
@@ -197,7 +216,7 @@ __global__ void __launch_bounds__(128)
       const bool dslow = fcol[i] != 0u;
       float h[4];
 #pragma unroll
-      for (int s2 = 0; s2 < 4; ++s2) h[s2] = hs[i * (SUB + 1) + lane + 32 * s2];
+      for (int s2 = 0; s2 < 4; ++s2) h[s2] = hs[i * SUB + lane + 32 * s2];
 #pragma unroll
       for (int r = 0; r < RW; ++r) {
         const float wi = __shfl_sync(0xffffffffu, w[r][s], l);
@@ -259,6 +278,8 @@ __global__ void __launch_bounds__(128)
       float* dst = ErrT + (err_col0 + c) * N + row0;
       if (RW == 4 && row0 + 4 <= N && ((N & 3) == 0)) {
         *reinterpret_cast<float4*>(dst) = make_float4(ev[0][s], ev[1 % RW][s], ev[2 % RW][s], ev[3 % RW][s]);
+      } else if (RW == 2 && row0 + 2 <= N && ((N & 1) == 0)) {
+        *reinterpret_cast<float2*>(dst) = make_float2(ev[0][s], ev[1 % RW][s]);
       } else {
 #pragma unroll
         for (int r = 0; r < RW; ++r)
@@ -271,7 +292,7 @@ __global__ void __launch_bounds__(128)
 // W[:, j0:j1] -= ErrT[e0:e0+KK, :]^T @ Hinv[r0:r0+KK, j0:j1]     exact fp32 FFMA, 128x128 tile, 8x8 per thread,
 // both operands k-major -> float4 global loads, register double buffering of the next 16-deep k chunk.
 template <bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     gptq_lazy_update_kernel(float* __restrict__ W, const float* __restrict__ ErrT, const float* __restrict__ Hinv,
                             int64_t N, int64_t C, int64_t e0, int64_t r0, int KK, int64_t j0, int64_t j1) {
   __shared__ __align__(16) float As[16][128];  // ErrT chunk [k][row]
@@ -395,7 +416,7 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     zero_dead_columns_kernel<<<fp_blocks, 256, 0, st>>>(W, N, C, dead_mask);
     WOQ_LAUNCH_CHECK();
   }
-  const int rows_per_cta = 4 * RW;
+  const int rows_per_cta = SUB_WARPS * RW;
   const bool vec = ((N & 3) == 0) && ((C & 3) == 0);
   for (int64_t i1 = 0; i1 < C; i1 += bs) {
     const int64_t i2 = std::min(i1 + bs, C);
@@ -410,13 +431,13 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     }
     for (int64_t c0 = i1; c0 < i2; c0 += SUB) {
       const int ncols = (int)std::min<int64_t>(SUB, i2 - c0);
-      const size_t smem = ((size_t)SUB * (SUB + 1) + 4 * SUB) * sizeof(float);
+      const size_t smem = ((size_t)SUB * SUB + 4 * SUB) * sizeof(float);
       static bool attr_set = false;
       if (!attr_set) {
         WOQ_CUDA(cudaFuncSetAttribute(gptq_subblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
       }
-      gptq_subblock_kernel<<<(unsigned)ceil_div(N, rows_per_cta), 128, smem, st>>>(
+      gptq_subblock_kernel<<<(unsigned)ceil_div(N, rows_per_cta), 32 * SUB_WARPS, smem, st>>>(
           W, Hinv, N, C, c0, ncols, per_channel ? 0 : g, G, maxq, scale, zero, codes, Q, ErrT, c0 - i1, losses);
       WOQ_LAUNCH_CHECK();
       const int64_t c1 = c0 + ncols;
