@@ -269,10 +269,33 @@ def gen_e2e():
     print("e2e: keys", [k for k in out if k not in ("init_state",)])
 
 
+def gen_hf_config():
+    """AutoGPTQ-style quantization_config the reference derives from a config mapping (save_load.py:1094-1156)."""
+    import json
+
+    from neural_compressor.torch.algorithms.weight_only.save_load import change_config_to_hf_format
+    from neural_compressor.torch.quantization import AWQConfig, GPTQConfig, RTNConfig
+
+    cases = {}
+    g = GPTQConfig(bits=4, group_size=128, use_sym=True, act_order=True, percdamp=0.02)
+    cases["gptq"] = dict(args=dict(kind="GPTQConfig", bits=4, group_size=128, use_sym=True, act_order=True, percdamp=0.02),
+                         out=change_config_to_hf_format({("model.layers.0.q_proj", "Linear"): g,
+                                                         ("lm_head", "Linear"): GPTQConfig(dtype="fp32")}))
+    r = RTNConfig(bits=8, group_size=32, use_sym=False)
+    cases["rtn"] = dict(args=dict(kind="RTNConfig", bits=8, group_size=32, use_sym=False),
+                        out=change_config_to_hf_format({("a", "Linear"): r}))
+    a = AWQConfig(bits=4, group_size=64, use_sym=True)
+    cases["awq"] = dict(args=dict(kind="AWQConfig", bits=4, group_size=64, use_sym=True),
+                        out=change_config_to_hf_format({("a", "Linear"): a}))
+    with open(os.path.join(OUT, "hf_quant_config.json"), "w") as f:
+        json.dump(cases, f, indent=1)
+    print("hf_config:", cases)
+
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rtn", "config1", "gptq", "awq", "e2e"]
+    which = sys.argv[1:] or ["rtn", "config1", "gptq", "awq", "e2e", "hf_config"]
     with torch.no_grad():
         if "rtn" in which:
             gen_rtn_pack()
@@ -284,3 +307,5 @@ if __name__ == "__main__":
             gen_awq_module()
         if "e2e" in which:
             gen_e2e()
+        if "hf_config" in which:
+            gen_hf_config()

@@ -1,0 +1,86 @@
+"""On-disk formats -- host logic only, no kernels: the HuggingFace layout written by `save` and read
+back by `load`, and the AutoGPTQ-style `quantization_config` (save_load.py:1094-1156 of the reference)."""
+import json
+import os
+
+import pytest
+import torch
+
+
+def tiny():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=4, vocab_size=128, max_position_embeddings=64, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    return LlamaForCausalLM(cfg).eval()
+
+
+def test_change_config_to_hf_format():
+    from neural_compressor_b200.algorithms.save_load import change_config_to_hf_format
+    from neural_compressor_b200.quantization import GPTQConfig, RTNConfig
+
+    g = GPTQConfig(bits=4, group_size=128, use_sym=True, act_order=True, percdamp=0.02)
+    fp = GPTQConfig(dtype="fp32")
+    got = change_config_to_hf_format({("model.layers.0.q_proj", "Linear"): g, ("model.layers.0.k_proj", "Linear"): g,
+                                      ("lm_head", "Linear"): fp})
+    assert got == {"bits": 4, "group_size": 128, "damp_percent": 0.02, "desc_act": True, "sym": True,
+                   "true_sequential": False, "model_name_or_path": None, "model_file_base_name": "model",
+                   "quant_method": "gptq"}
+    r = RTNConfig(bits=8, group_size=32, use_sym=False)
+    got = change_config_to_hf_format({("a", "Linear"): r})
+    assert (got["bits"], got["group_size"], got["sym"], got["damp_percent"], got["desc_act"]) == (8, 32, False, 0, False)
+    with pytest.raises(ValueError):  # a quantised lm_head cannot be written in this format
+        change_config_to_hf_format({("lm_head", "Linear"): r})
+    with pytest.raises(AssertionError):
+        change_config_to_hf_format({("a", "Linear"): r, ("b", "Linear"): RTNConfig(bits=4, group_size=32, use_sym=False)})
+
+
+def test_huggingface_format_roundtrip_cpu(tmp_path):
+    from neural_compressor_b200.algorithms import save_load
+    from neural_compressor_b200.algorithms.modules import B200WeightOnlyLinear
+    from neural_compressor_b200.quantization import RTNConfig
+    from neural_compressor_b200.utils import set_module
+
+    m = tiny()
+    cfg = RTNConfig(bits=4, group_size=32, use_sym=True)
+    qconfig = {}
+    gen = torch.Generator().manual_seed(1)
+    for name, mod in list(m.named_modules()):
+        if isinstance(mod, torch.nn.Linear) and name != "lm_head":
+            new = B200WeightOnlyLinear(mod.in_features, mod.out_features, bits=4, group_size=32, zp=True, device="cpu")
+            new.qweight = torch.randint(-2**31, 2**31 - 1, new.qweight.shape, generator=gen, dtype=torch.int64).to(torch.int32)
+            new.qzeros = torch.randint(-2**31, 2**31 - 1, new.qzeros.shape, generator=gen, dtype=torch.int64).to(torch.int32)
+            new.scales = torch.rand(new.scales.shape, generator=gen).half()
+            set_module(m, name, new)
+            qconfig[(name, "Linear")] = cfg
+    qconfig[("lm_head", "Linear")] = RTNConfig(dtype="fp32")
+    m.qconfig = qconfig
+    save_load.save(m, str(tmp_path), format="huggingface")
+    files = set(os.listdir(tmp_path))
+    assert {"config.json", "quantize_config.json"} <= files and any(f.endswith(".safetensors") for f in files)
+    qc = json.load(open(tmp_path / "quantize_config.json"))
+    assert qc["quant_method"] == "gptq" and qc["bits"] == 4 and qc["group_size"] == 32 and qc["sym"] is True
+    assert json.load(open(tmp_path / "config.json"))["quantization_config"]["bits"] == 4
+    m2 = save_load.load(str(tmp_path), format="huggingface", device="cpu")
+    s1, s2 = m.state_dict(), m2.state_dict()
+    assert set(s1) == set(s2)
+    for k in s1:
+        assert s1[k].dtype == s2[k].dtype and torch.equal(s1[k], s2[k]), k
+    assert isinstance(m2.model.layers[1].mlp.down_proj, B200WeightOnlyLinear)
+    assert isinstance(m2.lm_head, torch.nn.Linear)
+
+
+def test_hf_quant_config_matches_reference_fixture():
+    """tests/golden/hf_quant_config.json was written by the live reference (oracle/gen_golden.py hf_config)."""
+    import neural_compressor_b200.quantization as q
+    from neural_compressor_b200.algorithms.save_load import change_config_to_hf_format
+
+    cases = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hf_quant_config.json")))
+    for tag, case in cases.items():
+        args = dict(case["args"])
+        cfg = getattr(q, args.pop("kind"))(**args)
+        mapping = {("model.layers.0.q_proj", "Linear"): cfg}
+        if tag == "gptq":
+            mapping[("lm_head", "Linear")] = q.GPTQConfig(dtype="fp32")
+        assert change_config_to_hf_format(mapping) == case["out"], tag
