@@ -274,9 +274,28 @@ def bench_decode(dev, pk):
         base[name] = (r["qweight"], r["qzeros"], r["scales"], ops.build_stream_layout(r["qweight"], r["qzeros"], r["scales"],
                                                                                          4, 128, Kd, N))
     for _ in range(LAYERS):
-        packs.append({k: tuple(t.clone() for t in v) for k, v in base.items()})
+        blk = {k: tuple(t.clone() for t in v) for k, v in base.items()}
+        # what modules.SiblingGroup builds for q/k/v and gate/up: the members' strip-major layouts, concatenated
+        blk["qkv"] = torch.cat([blk[n][3] for n in ("q", "k", "v")])
+        blk["gateup"] = torch.cat([blk[n][3] for n in ("gate", "up")])
+        packs.append(blk)
     xh = torch.randn(1, HIDDEN, device=dev, dtype=torch.float16)
     yh = {n: torch.empty(1, N, device=dev, dtype=torch.float16) for n, N, _ in LINEARS}
+    yh["qkv"] = torch.empty(1, 3 * HIDDEN, device=dev, dtype=torch.float16)
+    yh["gateup"] = torch.empty(1, 2 * INTER, device=dev, dtype=torch.float16)
+
+    def token_fused(flags):
+        x = xh
+        for blk in packs:
+            ops.woq_linear_stream(x, blk["qkv"], None, 4, 128, HIDDEN, 3 * HIDDEN, out_dtype=torch.float16, flags=flags,
+                                  out=yh["qkv"])
+            ops.woq_linear_stream(x, blk["o"][3], None, 4, 128, HIDDEN, HIDDEN, out_dtype=torch.float16, flags=flags,
+                                  out=yh["o"])
+            ops.woq_linear_stream(x, blk["gateup"], None, 4, 128, HIDDEN, 2 * INTER, out_dtype=torch.float16, flags=flags,
+                                  out=yh["gateup"])
+            ops.woq_linear_stream(yh["gateup"][:, :INTER], blk["down"][3], None, 4, 128, INTER, HIDDEN,
+                                  out_dtype=torch.float16, flags=flags, out=yh["down"])
+            x = yh["down"]
 
     def token(flags, use_stream):
         x = xh
@@ -293,12 +312,14 @@ def bench_decode(dev, pk):
     res = {}
     by = sum(N * Kd // 2 + 2 * N * Kd // 128 + N * Kd // 256 + 2 * Kd + 2 * N for _, N, Kd in LINEARS) * LAYERS
     for flags, use_stream, tag in ((0, False, "optimum_layout"), (2, False, "optimum_layout_pdl"),
-                                   (0, True, "stream_layout"), (2, True, "stream_layout_pdl")):
-        token(flags, use_stream)
+                                   (0, True, "stream_layout"), (2, True, "stream_layout_pdl"),
+                                   (2, None, "stream_layout_pdl_siblings_fused")):
+        run = (lambda: token_fused(flags)) if use_stream is None else (lambda: token(flags, use_stream))
+        run()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            token(flags, use_stream)
+            run()
         for _ in range(3):
             graph.replay()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

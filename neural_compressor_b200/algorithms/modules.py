@@ -24,6 +24,7 @@ from .. import ops
 # Batches up to this many rows take the per-warp TMA-ring kernel on the derived stream layout (woq_stream.cu); larger
 # batches amortise the weight read over more rows and use the cluster split-K kernel on the optimum tensors.
 STREAM_MAX_ROWS = int(os.environ.get("B200WOQ_STREAM_MAX_ROWS", "4"))
+STREAM_FLAGS = 2 if os.environ.get("B200WOQ_PDL", "1") != "0" else 0  # bit 1: programmatic dependent launch
 
 
 class WeightOnlyLinear(torch.nn.Module):
@@ -129,27 +130,129 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
         return ops.dequantize(self.qweight, self.qzeros, self.scales, self.bits, self.group_size, self.in_features,
                               self.out_features, self.g_idx)
 
+    def _packed_key(self):
+        """Identity + version of the packed tensors: an in-place load_state_dict keeps the pointers but bumps versions."""
+        return tuple(v for t in (self.qweight, self.qzeros, self.scales) for v in (t.data_ptr(), t._version))
+
     def _stream_layout(self):
         """Lazily derived copy of the packed tensors in the B200 stream layout (not part of the state_dict)."""
-        key = (self.qweight.data_ptr(), self.qzeros.data_ptr(), self.scales.data_ptr())
+        key = self._packed_key()
         if getattr(self, "_stream_key", None) != key:
             self._stream = ops.build_stream_layout(self.qweight, self.qzeros, self.scales, self.bits, self.group_size,
                                                    self.in_features, self.out_features)
             self._stream_key = key
+            # the launch right after the build must not use programmatic dependent launch: the GEMV prefetches the
+            # layout before `griddepcontrol.wait`, which is only legal for data no in-flight kernel is still writing
+            self._stream_fresh = True
         return self._stream
+
+    def _stream_flags(self):
+        fresh, self._stream_fresh = getattr(self, "_stream_fresh", False), False
+        return 0 if fresh else STREAM_FLAGS
 
     def forward(self, input, input_scale=None):
         out_dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16) else torch.float32
         rows = input.numel() // self.in_features
         if (rows <= STREAM_MAX_ROWS and self.bits == 4 and self.g_idx is None and self.qweight.is_cuda
                 and os.environ.get("B200WOQ_STREAM", "1") != "0"):
+            group = getattr(self, "_siblings", None)
+            if group is not None and rows == 1 and input_scale is None:
+                return group.forward(self, input, out_dtype)
             layout = self._stream_layout()
             if layout is not None:
                 return ops.woq_linear_stream(input, layout, self.bias, self.bits, self.group_size, self.in_features,
-                                             self.out_features, input_scale=input_scale, out_dtype=out_dtype)
+                                             self.out_features, input_scale=input_scale, out_dtype=out_dtype,
+                                             flags=self._stream_flags())
         return ops.woq_linear(input, self.qweight, self.qzeros, self.scales, self.bias, self.bits, self.group_size,
                               self.in_features, self.out_features, g_idx=self.g_idx, input_scale=input_scale,
                               out_dtype=out_dtype)
+
+
+class SiblingGroup:
+    """Linears of one parent that read the same activation (q/k/v, gate/up).  At batch 1 a dequant-GEMV over a
+    4096x4096 layer is dominated by the ~2 us launch-to-launch dependency latency, not by its 8.7 MB of weights, so the
+    first member called with an input runs ONE launch over the concatenated column strips of all members (the stream
+    layout is strip-major, so concatenating the members' layouts is the fused layout) and the other members pick up
+    their slice when they are called with the very same tensor object.  Anything else (another tensor, a modified
+    tensor, batch > 1, an input scale) falls back to the member's own launch."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        self.offsets = []
+        n = 0
+        for m in self.members:
+            self.offsets.append(n)
+            n += m.out_features
+        self.out_features = n
+        self._key = None
+        self._x = None
+
+    def _fused(self):
+        key = tuple(v for m in self.members for t in (m.qweight, m.qzeros, m.scales, m.bias) for v in (t.data_ptr(), t._version))
+        if self._key != key:
+            parts = [ops.build_stream_layout(m.qweight, m.qzeros, m.scales, m.bits, m.group_size, m.in_features,
+                                             m.out_features) for m in self.members]
+            if any(p is None for p in parts):
+                self.layout = None
+            else:
+                self.layout = torch.cat(parts)
+                self.bias = torch.cat([m.bias.to(torch.float16) for m in self.members])
+                o = 0
+                for m, p in zip(self.members, parts):  # members alias their slice: no second copy of the weights
+                    m._stream = self.layout[o:o + p.numel()]
+                    m._stream_key = m._packed_key()
+                    m._stream_fresh = True
+                    o += p.numel()
+            self._key = key
+            self._fresh = True
+        return self.layout
+
+    def forward(self, member, x, out_dtype):
+        idx = self.members.index(member)
+        if self._x is x and self._ver == x._version and self._dtype == out_dtype and idx in self._pending:
+            y = self._y[..., self.offsets[idx]:self.offsets[idx] + member.out_features]
+            self._pending.discard(idx)
+            if not self._pending:
+                self._x = self._y = None
+            return y
+        layout = self._fused()
+        m0 = self.members[0]
+        if layout is None:
+            return ops.woq_linear(x, member.qweight, member.qzeros, member.scales, member.bias, member.bits,
+                                  member.group_size, member.in_features, member.out_features, out_dtype=out_dtype)
+        fresh, self._fresh = self._fresh, False
+        y = ops.woq_linear_stream(x, layout, self.bias, m0.bits, m0.group_size, m0.in_features, self.out_features,
+                                  out_dtype=out_dtype, flags=0 if fresh else STREAM_FLAGS)
+        self._x, self._ver, self._dtype, self._y = x, x._version, out_dtype, y
+        self._pending = set(range(len(self.members))) - {idx}
+        return y[..., self.offsets[idx]:self.offsets[idx] + member.out_features]
+
+
+SIBLING_PATTERNS = (("q_proj", "k_proj", "v_proj"), ("gate_proj", "up_proj"), ("w1", "w3"))
+
+
+def fuse_sibling_linears(model, patterns=SIBLING_PATTERNS):
+    """Attach a SiblingGroup to every parent whose children match one of `patterns` (attention q/k/v, gated-MLP
+    gate/up) and are packed 4-bit modules of equal in_features / group_size without g_idx.  Returns the number of
+    groups.  Disabled by B200WOQ_FUSE_SIBLINGS=0."""
+    if os.environ.get("B200WOQ_FUSE_SIBLINGS", "1") == "0":
+        return 0
+    n = 0
+    for parent in model.modules():
+        kids = dict(parent.named_children())
+        for pat in patterns:
+            ms = [kids.get(k) for k in pat]
+            if not all(isinstance(m, B200WeightOnlyLinear) for m in ms):
+                continue
+            m0 = ms[0]
+            if any(m.bits != 4 or m.g_idx is not None or m.in_features != m0.in_features or m.group_size != m0.group_size
+                   or m.out_features % 32 or not m.qweight.is_cuda for m in ms):
+                continue
+            group = SiblingGroup(ms)
+            for m in ms:
+                object.__setattr__(m, "_siblings", group)
+            n += 1
+    return n
 
 
 class MulLinear(torch.nn.Module):

@@ -127,6 +127,9 @@ def _load_huggingface(model_dir, device="cuda", **kwargs):
         model.tie_weights()
     model.config.quantization_config = qc
     model.eval()
+    from .modules import fuse_sibling_linears
+
+    fuse_sibling_linears(model)
     return model
 
 
@@ -187,4 +190,7 @@ def load(model_name_or_path, original_model=None, format="default", device="cuda
             new = MulLinear(new, torch.empty(in_f, device=device))
         set_module(model, op_name, new)
     model.load_state_dict(state, strict=False)
+    from .modules import fuse_sibling_linears
+
+    fuse_sibling_linears(model)
     return model

@@ -140,16 +140,18 @@ __global__ void __launch_bounds__(512) woq_gemm_stream_kernel(const Params p) {
   const int g = NI * 32;
   const int g0 = min(warp * p.gw_max, p.G);
   const int ngw = min(p.gw_max, p.G - g0);
-  // per-warp smem: [ ring: nst*rec ][ bars ][ xs: M rows x xs_ld f16 ][ zero pad: g+32 f16 ][ xsum: M*gw_max f32 ]
+  // per-warp smem: [ ring: nst*rec ][ bars ][ xs: M rows x xs_ld f16 ][ xsum: M*gw_max f32 ]; per CTA: red, zero pad
   const int nst = p.nst;
   const int rec_bytes = NI * 512 + 96;
   uint8_t* ring = smem_raw + (size_t)warp * p.warp_stride;
   const uint32_t ring_u32 = smem_u32(ring);
   const uint32_t bars = ring_u32 + nst * rec_bytes;
   __half* xs = reinterpret_cast<__half*>(ring + nst * rec_bytes + ((nst * 8 + 15) & ~15));
-  __half* zpad = xs + p.M * p.xs_ld;
-  float* xsum = reinterpret_cast<float*>(zpad + g + 32);
+  float* xsum = reinterpret_cast<float*>(xs + p.M * p.xs_ld);
   float* red = reinterpret_cast<float*>(smem_raw + (size_t)p.wpc * p.warp_stride);  // [wpc][M][32]
+  // g+32 zero halves read by the MMA lanes whose batch row does not exist.  Shared by the CTA: every warp stores the
+  // same zeros (benign) and only needs its own stores to be visible, so no CTA-wide barrier is required.
+  __half* zpad = reinterpret_cast<__half*>(red + (size_t)p.wpc * p.M * 32);
 
   const uint8_t* src = p.recs + ((size_t)strip * p.G + g0) * rec_bytes;
   if (lane == 0) {
@@ -365,7 +367,7 @@ __global__ void build_stream_kernel(const int32_t* __restrict__ qweight, const i
 }
 
 static size_t warp_smem_bytes(int M, int rec_bytes, int gw_max, int g, int nst) {
-  const size_t b = (size_t)nst * rec_bytes + ((nst * 8 + 15) & ~15) + (size_t)M * (gw_max * g + 32) * 2 + (g + 32) * 2 +
+  const size_t b = (size_t)nst * rec_bytes + ((nst * 8 + 15) & ~15) + (size_t)M * (gw_max * g + 32) * 2 +
                    (((size_t)M * gw_max + 3) & ~(size_t)3) * 4;
   return (b + 127) & ~(size_t)127;
 }
@@ -427,27 +429,40 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
   p.y = y;
   p.y_dtype = y_dtype;
   p.pdl = (flags & 2) ? 1 : 0;
-  // One CTA per 32-column strip; its wpc warps split K.  Pick wpc so that >= ~12 warps per SM are streaming and the
-  // ring depth so that every CTA of the grid is resident at once (a second wave would serialise behind the first).
+  // One CTA per 32-column strip; its wpc warps split K.  Every CTA of the grid must be resident at once (a second
+  // wave would serialise behind the first): that caps warps per CTA at 64 / ceil(strips / SMs) and shared memory per
+  // CTA at its share of the SM.  Within those caps: as many warps as keep >= 2 groups each (up to ~12 streaming warps
+  // per SM), then the deepest ring that fits.
   const int n_strips = (int)(N / 32);
   const int sms = num_sms();
   static const int env_wpc = getenv("B200WOQ_STREAM_WPC") ? atoi(getenv("B200WOQ_STREAM_WPC")) : 0;
   static const int env_nst = getenv("B200WOQ_STREAM_NST") ? atoi(getenv("B200WOQ_STREAM_NST")) : 0;
-  int wpc = 4;
-  while (wpc < 16 && (int64_t)n_strips * wpc < 12ll * sms && p.G / (wpc * 2) >= 2) wpc *= 2;
-  if (env_wpc > 0) wpc = env_wpc;
-  if (wpc > 16) wpc = 16;
-  while (wpc > 1 && p.G < wpc) wpc /= 2;
   const int cta_per_sm = (int)ceil_div(n_strips, sms);
-  const size_t budget = (size_t)(227 * 1024) / cta_per_sm - 1024;  // 1 KB reserved per CTA by the driver
+  size_t budget = (size_t)(227 * 1024) / cta_per_sm - 1024;  // 1 KB reserved per CTA by the driver
+  int wpc_cap = 16;
+  while (wpc_cap > 1 && wpc_cap * cta_per_sm > 64) wpc_cap /= 2;
   auto total_smem = [&](int w, int nst) {
-    return (size_t)w * warp_smem_bytes(p.M, p.rec_bytes, (int)ceil_div(p.G, w), g, nst) + (size_t)w * p.M * 32 * 4;
+    return (size_t)w * warp_smem_bytes(p.M, p.rec_bytes, (int)ceil_div(p.G, w), g, nst) + (size_t)w * p.M * 32 * 4 +
+           (size_t)(g + 32) * 2;
   };
-  int nst = (int)std::min<int64_t>(kMaxStages, ceil_div(p.G, wpc));
-  if (env_nst > 0) nst = std::min(env_nst, kMaxStages);
-  while (nst > 2 && total_smem(wpc, nst) > budget) --nst;
-  while (wpc < 16 && total_smem(wpc, nst) > 226 * 1024) wpc *= 2;  // more warps -> shorter x slices per warp
-  if (total_smem(wpc, nst) > 226 * 1024) {
+  int wpc = std::min(4, wpc_cap);
+  while (wpc < wpc_cap && (int64_t)n_strips * wpc < 12ll * sms && p.G / (wpc * 2) >= 2) wpc *= 2;
+  if (env_wpc > 0) wpc = std::min(env_wpc, 16);
+  while (wpc > 1 && p.G < wpc) wpc /= 2;
+  int nst = 0;
+  for (int pass = 0; pass < 2 && nst == 0; ++pass) {
+    for (int w = wpc; w >= 1 && nst == 0; w /= 2) {
+      const int need = (int)std::min<int64_t>(kMaxStages, ceil_div(p.G, w));
+      int n = env_nst > 0 ? std::min(env_nst, kMaxStages) : need;
+      while (n > std::min(2, need) && total_smem(w, n) > budget) --n;
+      if (total_smem(w, n) <= budget) {
+        wpc = w;
+        nst = n;
+      }
+    }
+    if (nst == 0) budget = 226 * 1024;  // cannot be single-wave: take what fits on an SM
+  }
+  if (nst == 0) {
     set_error("linear_forward_stream: K slice does not fit in shared memory");
     return B200WOQ_EUNSUPPORTED;
   }

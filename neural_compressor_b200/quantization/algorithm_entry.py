@@ -13,9 +13,13 @@ from .config import AWQ, GPTQ, RTN, SMOOTH_QUANT, AWQConfig, GPTQConfig, RTNConf
 
 
 def _bind_save(model):
+    """algorithm_entry.py:110-116 of the reference (model.save) + B200 inference set-up: packed q/k/v and gate/up
+    siblings get one fused batch-1 launch (modules.SiblingGroup; no effect until the model is converted)."""
+    from ..algorithms.modules import fuse_sibling_linears
     from ..algorithms.save_load import save
 
     model.save = MethodType(save, model)
+    fuse_sibling_linears(model)
 
 
 @register_algo(RTN)
