@@ -210,7 +210,10 @@ def run_b200(args):
         ach = sum(h_fl) / (sum(h_ms) / 1e3) / 1e12
         peak = pk["bf16_tflops_sustained"]
         roofline = dict(bound="tensor", kernel="hessian_syrk_tc_kernel (tcgen05 + TMA + TMEM)", achieved=round(ach, 1), peak=peak,
-                        unit="TFLOP/s", frac=round(ach / peak, 4), traffic=None, peak_source=pk["source"] + ", sustained",
+                        unit="TFLOP/s", frac=round(ach / peak, 4), traffic=syrk_traffic_per_launch(h_fl),
+                        traffic_source="dram__bytes_read.sum + dram__bytes_write.sum per launch, `ncu --set full` capture "
+                                       "summarised in profiles/ (launch-weighted mean over the C=4096 and C=11008 launches)",
+                        peak_source=pk["source"] + ", sustained",
                         launches=len(h_ms), avg_launch_ms=round(sum(h_ms) / len(h_ms), 4),
                         share_of_step=round(sum(h_ms) / ms_total, 3),
                         algorithmic="T*C*(C+128) flops per launch: the symmetric half of the reference's 2*T*C^2")
@@ -338,6 +341,22 @@ def bench_decode(dev, pk):
                 roofline_decode=dict(bound="hbm", kernel="woq_gemm_stream_kernel / woq_gemm_mma_kernel (best variant)", achieved=best["GBs"],
                                      peak=pk["hbm_gbs"], unit="GB/s", frac=round(best["GBs"] / pk["hbm_gbs"], 4),
                                      traffic=None, peak_source=pk["source"]))
+
+
+def syrk_traffic_per_launch(flops_per_launch):
+    """DRAM bytes per SYRK launch from the newest committed ncu capture (profiles/rNN_traffic.json), averaged over the
+    launches of the timed region (small grid = C 4096, large grid = C 11008).  None when no capture is committed."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r*_traffic.json")))
+    if not files or not flops_per_launch:
+        return None
+    by_grid = sorted(json.load(open(files[-1]))["dram_bytes_per_launch_by_grid"].values())
+    if len(by_grid) < 2:
+        return None
+    cut = (min(flops_per_launch) + max(flops_per_launch)) / 2
+    tot = sum(by_grid[-1] if f > cut else by_grid[0] for f in flops_per_launch)
+    return round(tot / len(flops_per_launch))
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm

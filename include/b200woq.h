@@ -115,11 +115,16 @@ int b200woq_linear_forward(const void* x, int x_dtype, int64_t M, int64_t K, int
                            const float* input_scale, void* y, int y_dtype, int bits, int group_size,
                            void* workspace, int64_t workspace_bytes, int flags, void* stream);
 
-/* Small-batch (M <= 16) 4-bit path on a derived, B200-native "stream layout" (woq_stream.cu): one contiguous
- * record per (128-column tile, group) = lane-ordered packed words + scales + decoded zero-points, streamed by TMA
- * bulk copies.  Built once per module from the optimum-format tensors (the reference likewise caches a derived
- * weight at first forward, modules.py:603-604).  b200woq_stream_layout_bytes returns 0 when the shape is not
- * eligible (bits != 4, group % 32, N % 32). */
+/* Decode-batch (M <= 4) 4-bit path on a derived, B200-native "stream layout" (woq_stream.cu): one contiguous
+ * 2144-byte record per (32-column strip, group) = lane-ordered packed words + 32 fp16 scales + 32 decoded
+ * zero-points, strips outermost; every warp streams its own records through a ring of cp.async.bulk copies.
+ * Because strips are outermost, the layouts of several linears that read the same activation (q/k/v, gate/up)
+ * concatenate into the layout of the fused [sum N, K] linear: one launch serves all of them.
+ * Built once per module from the optimum-format tensors (the reference likewise caches a derived weight at first
+ * forward, modules.py:603-604).  b200woq_stream_layout_bytes returns 0 when the shape is not eligible (bits != 4,
+ * group % 32, K % group, N % 32).  flags bit 1 = programmatic dependent launch: the kernel prefetches the layout
+ * before griddepcontrol.wait, so the flag is only legal when no in-flight kernel is still WRITING the layout (the
+ * Python module clears it for the first launch after a build). */
 int64_t b200woq_stream_layout_bytes(int64_t N, int64_t K, int bits, int group_size);
 int b200woq_build_stream_layout(const int32_t* qweight, const int32_t* qzeros, const void* scales16, int64_t N,
                                 int64_t K, int bits, int group_size, void* out, void* stream);
