@@ -24,6 +24,9 @@ from .. import ops
 # Batches up to this many rows take the per-warp TMA-ring kernel on the derived stream layout (woq_stream.cu); larger
 # batches amortise the weight read over more rows and use the cluster split-K kernel on the optimum tensors.
 STREAM_MAX_ROWS = int(os.environ.get("B200WOQ_STREAM_MAX_ROWS", "4"))
+# Above this many rows the fused dequant-GEMM kernels (tuned for the HBM-bound decode regime) hand over to
+# dequantize + cuBLAS.
+GEMM_MAX_ROWS = int(os.environ.get("B200WOQ_GEMM_MAX_ROWS", "64"))
 STREAM_FLAGS = 2 if os.environ.get("B200WOQ_PDL", "1") != "0" else 0  # bit 1: programmatic dependent launch
 
 
@@ -163,6 +166,13 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
                 return ops.woq_linear_stream(input, layout, self.bias, self.bits, self.group_size, self.in_features,
                                              self.out_features, input_scale=input_scale, out_dtype=out_dtype,
                                              flags=self._stream_flags())
+        if rows > GEMM_MAX_ROWS:
+            # prefill / calibration batches are compute-bound: recover the fp16 weight once (K4 dequantize kernel) and
+            # run a plain library GEMM in the input's dtype -- literally the reference's forward (modules.py:594-610:
+            # recover() then F.linear), so calibration forwards through already-packed modules keep fp32 activations
+            w = self.recover().to(input.dtype)
+            x = input if input_scale is None else input * input_scale.to(input.dtype)
+            return torch.nn.functional.linear(x, w, None if self.bias is None else self.bias.to(input.dtype))
         return ops.woq_linear(input, self.qweight, self.qzeros, self.scales, self.bias, self.bits, self.group_size,
                               self.in_features, self.out_features, g_idx=self.g_idx, input_scale=input_scale,
                               out_dtype=out_dtype)

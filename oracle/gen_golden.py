@@ -269,6 +269,68 @@ def gen_e2e():
     print("e2e: keys", [k for k in out if k not in ("init_state",)])
 
 
+OPTION_CASES = [
+    # (tag, algo, config kwargs) -- the option surface of the reference's own test matrix (test_rtn.py:106-165,
+    # test_gptq.py:106-185, test_awq.py:60-84) on the tiny Llama; RTN must be bit-exact, GPTQ/AWQ within tolerance
+    ("rtn_b8_perchannel", "rtn", dict(bits=8, group_size=-1, use_sym=True)),
+    ("rtn_b8_asym", "rtn", dict(bits=8, group_size=32, use_sym=False)),
+    ("rtn_b4_full_range", "rtn", dict(bits=4, group_size=32, use_sym=True, use_full_range=True)),
+    ("rtn_b4_mse_search", "rtn", dict(bits=4, group_size=32, use_sym=False, use_mse_search=True)),
+    ("rtn_b3", "rtn", dict(bits=3, group_size=32, use_sym=True)),
+    ("rtn_b2_asym", "rtn", dict(bits=2, group_size=64, use_sym=False)),
+    ("rtn_lm_head", "rtn", dict(bits=4, group_size=128, use_sym=True, quant_lm_head=True)),
+    ("rtn_dtype_int8", "rtn", dict(dtype="int8", group_size=32, use_sym=True)),
+    ("gptq_b8", "gptq", dict(bits=8, group_size=32, use_sym=True, block_size=128)),
+    ("gptq_perchannel", "gptq", dict(bits=4, group_size=-1, use_sym=True, block_size=128)),
+    ("gptq_mse_search", "gptq", dict(bits=4, group_size=32, use_sym=False, use_mse_search=True, block_size=128)),
+    ("gptq_act_order", "gptq", dict(bits=4, group_size=32, use_sym=True, act_order=True, block_size=128)),
+    ("gptq_true_sequential", "gptq", dict(bits=4, group_size=32, use_sym=True, true_sequential=True, block_size=128)),
+    ("gptq_b3", "gptq", dict(bits=3, group_size=32, use_sym=False, block_size=128)),
+    ("awq_sym_noclip", "awq", dict(bits=4, group_size=32, use_sym=True, use_auto_clip=False)),
+    ("awq_noscale", "awq", dict(bits=4, group_size=32, use_sym=False, use_auto_scale=False)),
+]
+
+
+def gen_options():
+    """Option matrix through the reference's public API (one fixture entry per OPTION_CASES row) + a Conv1D model."""
+    from neural_compressor.torch.quantization import AWQConfig, GPTQConfig, RTNConfig, convert, prepare, quantize
+
+    ids = calib_ids()
+    probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
+
+    def run_fn(model):
+        for x in ids:
+            model(x)
+
+    out = dict(cases={})
+    for tag, algo, kw in OPTION_CASES:
+        m = tiny_llama()
+        if algo == "rtn":
+            m = convert(prepare(m, RTNConfig(use_layer_wise=False, **kw)))
+        elif algo == "gptq":
+            m = prepare(m, GPTQConfig(model_path="/tmp", **kw))
+            run_fn(m)
+            m = convert(m)
+        else:
+            m = quantize(m, AWQConfig(**kw), run_fn=run_fn, example_inputs=ids[0])
+        with torch.no_grad():
+            out["cases"][tag] = dict(algo=algo, kw=kw, state=woq_state(m), logits=m(probe).logits.clone())
+        print("options:", tag, len(out["cases"][tag]["state"]), "tensors")
+    # GPT-2 style model: transformers.Conv1D weights are [in, out] (rtn.py:209-216 transpose handling)
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    torch.manual_seed(0)
+    g2 = GPT2LMHeadModel(GPT2Config(n_embd=64, n_layer=2, n_head=2, vocab_size=256, n_positions=64)).eval()
+    out["gpt2_init"] = {k: v.clone() for k, v in g2.state_dict().items()}
+    p2 = torch.randint(0, 256, (1, 16), generator=torch.Generator().manual_seed(5))
+    out["gpt2_probe"] = p2
+    g2 = convert(prepare(g2, RTNConfig(bits=4, group_size=32, use_sym=False, use_layer_wise=False)))
+    with torch.no_grad():
+        out["gpt2_rtn"] = dict(state=woq_state(g2), logits=g2(p2).logits.clone(),
+                               module_types={n: type(x).__name__ for n, x in g2.named_modules()})
+    torch.save(out, os.path.join(OUT, "options_matrix.pt"))
+
+
 def gen_hf_config():
     """AutoGPTQ-style quantization_config the reference derives from a config mapping (save_load.py:1094-1156)."""
     import json
@@ -295,7 +357,7 @@ def gen_hf_config():
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["rtn", "config1", "gptq", "awq", "e2e", "hf_config"]
+    which = sys.argv[1:] or ["rtn", "config1", "gptq", "awq", "e2e", "hf_config", "options"]
     with torch.no_grad():
         if "rtn" in which:
             gen_rtn_pack()
@@ -309,3 +371,5 @@ if __name__ == "__main__":
             gen_e2e()
         if "hf_config" in which:
             gen_hf_config()
+        if "options" in which:
+            gen_options()

@@ -51,3 +51,8 @@ def golden_config1():
 @pytest.fixture(scope="session")
 def golden_e2e():
     return load_golden("e2e_tiny_llama.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_options():
+    return load_golden("options_matrix.pt")

