@@ -70,6 +70,33 @@ def recover_forward(model):
     return model
 
 
+class _Chunks(list):
+    """Per-sample activations regrouped into a few large batches; `weights[i]` = samples in chunk i."""
+
+    weights = None
+
+
+def _rebatch(samples, max_tokens=None):
+    """The reference evaluates every candidate scale / clip ratio sample by sample (awq.py:509-545): 128 small GEMMs
+    and 128 reductions per candidate, launch-bound on a GPU.  Samples of identical shape are stacked into chunks of up
+    to B200WOQ_AWQ_CHUNK_TOKENS tokens; `sum_s mean_s(err^2)` becomes `sum_chunks w * mean_chunk(err^2)`, the same value
+    (fp64 accumulation).  Ragged calibration sets keep the per-sample path."""
+    import os
+
+    if max_tokens is None:
+        max_tokens = int(os.environ.get("B200WOQ_AWQ_CHUNK_TOKENS", "65536"))
+    if len(samples) < 2 or max_tokens <= 0 or any(x.shape != samples[0].shape or x.dim() < 2 for x in samples):
+        return samples
+    per = max(1, max_tokens // max(1, samples[0].numel() // samples[0].shape[-1]))
+    out = _Chunks()
+    out.weights = []
+    for i in range(0, len(samples), per):
+        grp = samples[i:i + per]
+        out.append(torch.cat(grp, dim=0))
+        out.weights.append(float(len(grp)))
+    return out
+
+
 class ActAwareWeightQuant:
     """awq.py:157-545."""
 
@@ -127,7 +154,8 @@ class ActAwareWeightQuant:
 
     @staticmethod
     def module_inference(module, inputs) -> List[torch.Tensor]:
-        outs = []
+        outs = _Chunks()
+        outs.weights = getattr(inputs, "weights", None)
         for inp in inputs:
             out = module(inp)
             outs.append(out[0] if isinstance(out, tuple) else out)
@@ -152,13 +180,21 @@ class ActAwareWeightQuant:
         self.block_inference(block)
         for h in handles:
             h.remove()
-        return store
+        return {n: _rebatch(v) for n, v in store.items()}
 
     @staticmethod
     def _loss(org: List[torch.Tensor], cur: List[torch.Tensor]) -> float:
         acc = torch.zeros(1, dtype=torch.float64, device=org[0].device)
-        for a, b in zip(org, cur):
-            ops.mse_accumulate(a, b, acc)
+        weights = getattr(org, "weights", None)
+        if weights is None:
+            for a, b in zip(org, cur):
+                ops.mse_accumulate(a, b, acc)
+            return acc.item()
+        part = torch.zeros_like(acc)
+        for a, b, w in zip(org, cur, weights):  # a chunk of w equal-length samples: w * mean = sum of the w sample means
+            part.zero_()
+            ops.mse_accumulate(a, b, part)
+            acc += w * part
         return acc.item()
 
     # ------------------------------------------------------------------ the algorithm

@@ -287,7 +287,7 @@ class MulLinear(torch.nn.Module):
     def forward(self, X):
         if isinstance(self.linear, B200WeightOnlyLinear):
             return self.linear(X, input_scale=self.input_scale.float())
-        return self.linear(torch.mul(X, self.input_scale))
+        return self.linear(torch.mul(X, self.input_scale.to(X.dtype)))  # statistics are fp32 here; keep the model's dtype
 
     def _update_linear(self):
         scale = self.input_scale.view(1, self.input_scale.shape[0])

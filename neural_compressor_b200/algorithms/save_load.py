@@ -57,8 +57,9 @@ def _save_huggingface(model, output_dir, **kwargs):
     quantization_config = model.config.quantization_config
     if not isinstance(quantization_config, dict):
         quantization_config = quantization_config.to_dict()
-    model.save_pretrained(output_dir, max_shard_size=kwargs.get("max_shard_size", "5GB"),
-                          safe_serialization=kwargs.get("safe_serialization", True))
+    # the class's method: `model.save_pretrained` may itself be bound to this function (transformers entry)
+    type(model).save_pretrained(model, output_dir, max_shard_size=kwargs.get("max_shard_size", "5GB"),
+                                safe_serialization=kwargs.get("safe_serialization", True))
     with open(os.path.join(output_dir, HF_QUANT_CONFIG_NAME), "w", encoding="utf-8") as f:
         json.dump(quantization_config, f, indent=2)
     if getattr(model, "generation_config", None) is not None:
