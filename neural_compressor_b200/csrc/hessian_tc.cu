@@ -6,16 +6,21 @@
 // SWIZZLE_128B UMMA layout:  ((8,8,m),(8,k)) : ((1,8,LBO),(64,SBO))  elements,  LBO = BK*128 B (next 64 channels),
 // SBO = 1024 B (next 8 tokens).  No transposes, no ldmatrix: the slabs stream HBM/L2 -> smem -> tensor core.
 //
-//   tile        128 (i) x 256 (j) fp32 accumulator = 256 TMEM columns, one CTA per tile, tiles with 128-row block
-//               ti <= 2*tj+1 only (SYRK: upper block triangle, the rest is mirrored in b200woq_hessian_finalize)
+//   tile        default: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns a 256 x 256 tile, each CTA keeps the
+//               128 x 256 fp32 accumulator of its rows in TMEM and stages its 128 A rows + half of the B columns
+//               (hessian_syrk_tc2_kernel below).  B200WOQ_SYRK_PAIR=0: one CTA per 128 x 256 tile
+//               (hessian_syrk_tc_kernel).  Only tiles touching the upper block triangle are computed; the rest is
+//               mirrored in b200woq_hessian_finalize.
 //   precision   the tensor core adds into its fp32 accumulator with truncation, so a long contraction drifts
 //               (measured 1.3e-5 relative after 8192 tokens).  The token loop is therefore cut into SEGMENTS of 2048
 //               tokens; each segment accumulates in its own TMEM buffer (2 x 256 columns, double buffered) and is
 //               added to the fp32 H in global memory with round-to-nearest while the next segment's MMAs run.
-//   pipeline    4 stages x (A: 2 boxes, B: 4 boxes) = 48 KB per stage, mbarrier full/empty ring
-//   warp roles  warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer (1 lane), warps 2-5 = epilogue
-//   MMA         tcgen05.mma.cta_group::1.kind::f16, M=128, N=256, K=16, both operands MN-major, fp32 accumulate
-//   epilogue    tcgen05.ld 32x32b.x32 -> registers -> read-modify-write of the fp32 H tile (owned by this CTA)
+//   pipeline    mbarrier full/empty ring of [64 tokens x 64 channels] SWIZZLE_128B boxes: 6 stages x 32 KB per CTA in
+//               pair mode (4 x 48 KB in 1-CTA mode)
+//   warp roles  warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer (1 lane, even CTA only in pair
+//               mode), warps 2-5 = epilogue
+//   MMA         tcgen05.mma.kind::f16, K=16, both operands MN-major, fp32 accumulate; M=256/N=256 over the pair
+//   epilogue    tcgen05.ld 32x32b.x32 -> registers -> read-modify-write of the fp32 H tile rows owned by this CTA
 //
 // fp16 x fp16 (11-bit mantissas) products are exact in fp32, so one pass is fp32-grade.
 #include <cuda.h>
@@ -38,6 +43,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES; // 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NUM_EPI_THREADS = 128;
 constexpr int kSuperRowsDefault = 16;  // row tiles per rasterisation super-row
+constexpr int kPairDefault = 1;        // CTA-pair (cta_group::2) kernel by default; B200WOQ_SYRK_PAIR=0 selects the 1-CTA kernel
 constexpr int TMEM_COLS = 512;      // two 128x256 fp32 accumulators
 constexpr int SEG_KB = 32;          // k-blocks (of BK tokens) per accumulation segment = 2048 tokens
 
@@ -240,6 +246,185 @@ __global__ void __launch_bounds__(192, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on one TPC owns a 256 x 256 tile.  CTA r stages ITS 128
+// rows of the A panel and HALF of the B panel (128 of the 256 columns); the pair's MMA (M = 256, N = 256, issued by the
+// even CTA only) reads A from each CTA's own shared memory and the B halves from both, so every CTA pulls 32 KB per
+// 64-token stage through L2 instead of 48 KB for the same flops -- the 1-CTA kernel is bound by exactly that traffic.
+// Barriers: full[s] lives in the even CTA and collects the TMA bytes of BOTH CTAs; empty[s] / accum_full[b] are
+// arrived on in both CTAs by a multicast tcgen05.commit; accum_empty[b] (even CTA) counts the epilogue threads of both.
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = (128 / 64) * BOX_BYTES;   // 16 KB: this CTA's 128 rows
+constexpr int B2_BYTES = (128 / 64) * BOX_BYTES;   // 16 KB: this CTA's half of the 256 columns
+constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;  // 32 KB
+constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the even CTA of a pair (cute: Sm100MmaPeerBitMask)
+constexpr int kSuperRows2Default = 8;
+
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_even_cta, int c_inner,
+                                                 int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_even_cta), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {  // arrives on `bar` at the same offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// grid = 2 CTAs per 256 x 256 tile of the super-row enumeration; cluster (2,1,1); block = 192 threads
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+    hessian_syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t Ttok, int64_t C, float* __restrict__ H,
+                            uint32_t idesc, int super_rows) {
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  int id = blockIdx.x >> 1, ti0 = 0, rows;
+  const int nt = (int)((C + 255) / 256);
+  for (;;) {
+    rows = min(super_rows, nt - ti0);
+    const int cnt = rows * (nt - ti0);  // column tiles tj >= ti0 for every row of the super-row
+    if (id < cnt) break;
+    id -= cnt;
+    ti0 += super_rows;
+  }
+  const int tj = ti0 + id / rows, ti = ti0 + id % rows;
+  if (ti > tj) return;  // strictly below the block diagonal (both CTAs of the pair leave together)
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES2 * STAGE2_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES2 + s); };
+  auto accum_full = [&](int b) { return bars + 8u * (2 * STAGES2 + b); };
+  auto accum_empty = [&](int b) { return bars + 8u * (2 * STAGES2 + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES2 + 4);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t i0 = (int64_t)ti * 256 + 128 * rank;  // this CTA's accumulator rows
+  const int64_t j0 = (int64_t)tj * 256;               // the pair's columns
+  const int nk = (int)((Ttok + BK - 1) / BK);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accum_full(b), 1);
+      mbar_init(accum_empty(b), 2 * NUM_EPI_THREADS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across the pair
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; ++kb) {
+        const int s = kb % STAGES2;
+        const uint32_t ph = (uint32_t)(kb / STAGES2) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        if (rank == 0) mbar_expect_tx(full_bar(s), 2 * STAGE2_BYTES);  // the bytes of both CTAs land on this barrier
+        const uint32_t sa = base + s * STAGE2_BYTES;
+        const uint32_t fb = full_bar(s) & kPeerBitMask;
+        const int t0 = kb * BK;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) tma_load_2d_pair(sa + b * BOX_BYTES, &tmap, fb, (int)(i0 + 64 * b), t0);
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+          tma_load_2d_pair(sa + A2_BYTES + b * BOX_BYTES, &tmap, fb, (int)(j0 + 128 * rank + 64 * b), t0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      const int nseg = (nk + SEG_KB - 1) / SEG_KB;
+      for (int seg = 0; seg < nseg; ++seg) {
+        const int b = seg & 1;
+        mbar_wait(accum_empty(b), ((uint32_t)(seg >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(b * 256);
+        const int kb1 = min(nk, (seg + 1) * SEG_KB);
+        for (int kb = seg * SEG_KB; kb < kb1; ++kb) {
+          const int s = kb % STAGES2;
+          const uint32_t ph = (uint32_t)(kb / STAGES2) & 1u;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * STAGE2_BYTES;
+#pragma unroll
+          for (int k4 = 0; k4 < BK / 16; ++k4) {
+            const uint64_t ad = make_desc(sa + k4 * 2048);
+            const uint64_t bd = make_desc(sa + A2_BYTES + k4 * 2048);
+            umma_f16_pair(tmem_d, ad, bd, idesc, (kb != seg * SEG_KB || k4 != 0) ? 1u : 0u);
+          }
+          umma_commit_pair(empty_bar(s));
+        }
+        umma_commit_pair(accum_full(b));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int64_t row = i0 + q * 32 + lane;
+    const int nseg = (nk + SEG_KB - 1) / SEG_KB;
+    for (int seg = 0; seg < nseg; ++seg) {
+      const int b = seg & 1;
+      mbar_wait(accum_full(b), (uint32_t)(seg >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int cc = 0; cc < 256 / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + cc * 32), r);
+        const int64_t col0 = j0 + cc * 32;
+        if (row < C && col0 < C) {
+          float* dst = H + row * C + col0;
+          if (col0 + 32 <= C && ((C & 3) == 0)) {
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+              float4 h = *reinterpret_cast<float4*>(dst + 4 * v);
+              h.x += __uint_as_float(r[4 * v + 0]);
+              h.y += __uint_as_float(r[4 * v + 1]);
+              h.z += __uint_as_float(r[4 * v + 2]);
+              h.w += __uint_as_float(r[4 * v + 3]);
+              *reinterpret_cast<float4*>(dst + 4 * v) = h;
+            }
+          } else {
+            for (int v = 0; v < 32; ++v)
+              if (col0 + v < C) dst[v] += __uint_as_float(r[v]);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(accum_empty(b) & kPeerBitMask) : "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync_all();  // nobody leaves while the peer may still signal its barriers or read its shared memory
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -286,6 +471,25 @@ int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C,
   if (!attr_set) {
     WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
+  }
+  static const int pair_mode = getenv("B200WOQ_SYRK_PAIR") ? atoi(getenv("B200WOQ_SYRK_PAIR")) : kPairDefault;
+  if (pair_mode) {
+    static const int super_rows2 =
+        getenv("B200WOQ_SYRK_SUPER_ROWS") ? std::max(1, atoi(getenv("B200WOQ_SYRK_SUPER_ROWS"))) : kSuperRows2Default;
+    // cta_group::2: M = 256 (128 rows per CTA), N = 256
+    const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
+                            ((uint32_t)(256 >> 4) << 24);
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
+      attr2_set = true;
+    }
+    const int nt = (int)ceil_div(C, 256);
+    unsigned tiles = 0;
+    for (int ti0 = 0; ti0 < nt; ti0 += super_rows2) tiles += (unsigned)(std::min(super_rows2, nt - ti0) * (nt - ti0));
+    hessian_syrk_tc2_kernel<<<2 * tiles, 192, SMEM2_BYTES, st>>>(tmap, T, C, Hsum, idesc2, super_rows2);
+    WOQ_LAUNCH_CHECK();
+    return 0;
   }
   static const int super_rows =
       getenv("B200WOQ_SYRK_SUPER_ROWS") ? std::max(1, atoi(getenv("B200WOQ_SYRK_SUPER_ROWS"))) : kSuperRowsDefault;
