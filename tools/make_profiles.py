@@ -25,6 +25,13 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 import ncu_summary  # noqa: E402
 
 
+NOTES = {
+    "r01": "This list was captured before the round's last two kernel changes (CTA-pair SYRK: -7 % per launch; 8-warp GPTQ\n"
+           "column loop + 2-CTA/SM lazy update: -28 % per layer), so K1/K3 shares are slightly lower in the final build\n"
+           "(step 460 -> 420 ms); the per-kernel captures next to this file are from the final build.\n",
+}
+
+
 def launch_share(rnd):
     src = os.path.join(ROOT, "gpurun_out", f"{rnd}_launches.csv")
     if not os.path.exists(src):
@@ -51,7 +58,8 @@ def launch_share(rnd):
         f.write(f"# {rnd}: kernel share of one timed step (one Llama-2-7B decoder block of GPTQ calibration)\n\n")
         f.write("Source: `ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include \"timed_steps/\"` around\n"
                 "`python bench.py --steps 1 --warmup 1 --no-e2e --no-decode --no-cpu-baseline` (tools/profile_round.sh); the raw\n"
-                f"launch list is `{rnd}_launches.csv.gz`.  Durations are serialised, cold-cache per-launch times: read the SHARES.\n\n")
+                f"launch list is `{rnd}_launches.csv.gz`.  Durations are serialised, cold-cache per-launch times: read the SHARES.\n"
+                + NOTES.get(rnd, "") + "\n")
         f.write(f"{n} launches, {tot:.1f} ms of kernel time; hand-written b200woq kernels: {ours:.1f} ms ({100 * ours / tot:.1f} %), the rest is\n"
                 "the model's own forward (cuBLAS `nvjet` GEMMs, SDPA, torch elementwise) and cuSOLVER/cuBLAS inside the Cholesky chain.\n\n")
         f.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
