@@ -17,6 +17,8 @@
 // shared memory for the whole sub-block.
 #include <climits>
 
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace b200woq {
@@ -129,7 +131,8 @@ __global__ void __launch_bounds__(32 * SUB_WARPS)
     gptq_subblock_kernel(float* __restrict__ W, const float* __restrict__ Hinv, int64_t N, int64_t C, int64_t c0,
                          int ncols, int g, int64_t G, float maxq, const float* __restrict__ scale,
                          const float* __restrict__ zero, uint8_t* __restrict__ codes, float* __restrict__ Q,
-                         float* __restrict__ ErrT, int64_t err_col0, float* __restrict__ losses) {
+                         float* __restrict__ ErrT, int64_t err_col0, float* __restrict__ losses,
+                         float* __restrict__ ErrT_hi, float* __restrict__ ErrT_lo) {
   extern __shared__ __align__(16) float hs[];  // [ncols][SUB] upper-triangular diagonal block of Hinv, then 4 x [SUB] column constants
   float* dcol = hs + SUB * SUB;
   float* rcol = dcol + SUB;
@@ -276,6 +279,15 @@ __global__ void __launch_bounds__(32 * SUB_WARPS)
     const int c = lane + 32 * s;
     if (c < ncols) {
       float* dst = ErrT + (err_col0 + c) * N + row0;
+      if (ErrT_hi) {  // TF32 split for the tensor-core lazy update (gptq_tc.cu): hi is TF32-exact, lo = e - hi
+#pragma unroll
+        for (int r = 0; r < RW; ++r)
+          if (row0 + r < N) {
+            const float hi = __uint_as_float(__float_as_uint(ev[r][s]) & 0xffffe000u);
+            ErrT_hi[(err_col0 + c) * N + row0 + r] = hi;
+            ErrT_lo[(err_col0 + c) * N + row0 + r] = ev[r][s] - hi;
+          }
+      }
       if (RW == 4 && row0 + 4 <= N && ((N & 3) == 0)) {
         *reinterpret_cast<float4*>(dst) = make_float4(ev[0][s], ev[1 % RW][s], ev[2 % RW][s], ev[3 % RW][s]);
       } else if (RW == 2 && row0 + 2 <= N && ((N & 1) == 0)) {
@@ -379,11 +391,33 @@ __global__ void __launch_bounds__(256, 2)
 
 }  // namespace b200woq
 
+namespace b200woq {
+// gptq_tc.cu: tensor-core (3 x TF32 split) lazy update
+struct LazyTcPlan {
+  CUtensorMap maps[4];
+  bool ok;
+};
+bool lazy_tc_shape_ok(int64_t N, int64_t C);
+int lazy_tc_split(const float* x, float* hi, float* lo, int64_t n, cudaStream_t st);
+int lazy_tc_make_plan(LazyTcPlan* plan, const float* e_hi, const float* e_lo, int64_t err_rows, int64_t N, const float* h_hi,
+                      const float* h_lo, int64_t C);
+int lazy_tc_update(const LazyTcPlan* plan, float* W, int64_t N, int64_t C, int64_t e0, int64_t r0, int KK, int64_t j0,
+                   int64_t j1, cudaStream_t st);
+}  // namespace b200woq
+
 using namespace b200woq;
 
+static bool lazy_tc_enabled() {
+  static const int v = getenv("B200WOQ_LAZY_TC") ? atoi(getenv("B200WOQ_LAZY_TC")) : 0;
+  return v != 0;
+}
+
+// [ErrT bs x N] and, for the tensor-core lazy update, [ErrT_hi][ErrT_lo] (bs x N each) + [Hinv_hi][Hinv_lo] (C x C each)
 extern "C" int64_t b200woq_gptq_workspace_bytes(int64_t N, int64_t C, int blocksize) {
   const int64_t bs = blocksize <= 0 ? C : (blocksize > C ? C : blocksize);
-  return N * bs * (int64_t)sizeof(float) + 256;
+  int64_t floats = N * bs;
+  if (lazy_tc_enabled() && bs < C && lazy_tc_shape_ok(N, C)) floats += 2 * N * bs + 2 * C * C;
+  return floats * (int64_t)sizeof(float) + 256;
 }
 
 extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8_t* dead_mask, int64_t N, int64_t C,
@@ -400,6 +434,21 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     return B200WOQ_EWORKSPACE;
   }
   float* ErrT = (float*)workspace;  // [bs, N]  (transposed: the lazy GEMM reads it k-major)
+  const bool use_tc = lazy_tc_enabled() && bs < C && lazy_tc_shape_ok(N, C);
+  float *ErrT_hi = nullptr, *ErrT_lo = nullptr;
+  LazyTcPlan plan;
+  plan.ok = false;
+  if (use_tc) {
+    ErrT_hi = ErrT + N * bs;
+    ErrT_lo = ErrT_hi + N * bs;
+    float* H_hi = ErrT_lo + N * bs;
+    float* H_lo = H_hi + C * C;
+    if (int rc = lazy_tc_split(Hinv, H_hi, H_lo, C * C, st)) return rc;
+    if (lazy_tc_make_plan(&plan, ErrT_hi, ErrT_lo, bs, N, H_hi, H_lo, C) != 0) {
+      plan.ok = false;
+      ErrT_hi = ErrT_lo = nullptr;
+    }
+  }
   const float maxq = (float)((1 << bits) - 1);
   const bool per_channel = groupsize <= 0;
   const int g = per_channel ? (int)C : groupsize;
@@ -438,12 +487,15 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
         attr_set = true;
       }
       gptq_subblock_kernel<<<(unsigned)ceil_div(N, rows_per_cta), 32 * SUB_WARPS, smem, st>>>(
-          W, Hinv, N, C, c0, ncols, per_channel ? 0 : g, G, maxq, scale, zero, codes, Q, ErrT, c0 - i1, losses);
+          W, Hinv, N, C, c0, ncols, per_channel ? 0 : g, G, maxq, scale, zero, codes, Q, ErrT, c0 - i1, losses, ErrT_hi,
+          ErrT_lo);
       WOQ_LAUNCH_CHECK();
       const int64_t c1 = c0 + ncols;
       if (c1 < i2) {  // in-block propagation to the rest of the block
         dim3 grid((unsigned)ceil_div(i2 - c1, 128), (unsigned)ceil_div(N, 128));
-        if (vec && (c1 & 3) == 0)
+        if (plan.ok && (ncols % 8) == 0 && (c1 & 3) == 0) {
+          if (int rc = lazy_tc_update(&plan, W, N, C, c0 - i1, c0, ncols, c1, i2, st)) return rc;
+        } else if (vec && (c1 & 3) == 0)
           gptq_lazy_update_kernel<true><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, c0 - i1, c0, ncols, c1, i2);
         else
           gptq_lazy_update_kernel<false><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, c0 - i1, c0, ncols, c1, i2);
@@ -452,7 +504,9 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     }
     if (i2 < C) {  // gptq.py:1304
       dim3 grid((unsigned)ceil_div(C - i2, 128), (unsigned)ceil_div(N, 128));
-      if (vec && (i2 & 3) == 0)
+      if (plan.ok && ((i2 - i1) % 8) == 0 && (i2 & 3) == 0) {
+        if (int rc = lazy_tc_update(&plan, W, N, C, 0, i1, (int)(i2 - i1), i2, C, st)) return rc;
+      } else if (vec && (i2 & 3) == 0)
         gptq_lazy_update_kernel<true><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, 0, i1, (int)(i2 - i1), i2, C);
       else
         gptq_lazy_update_kernel<false><<<grid, 256, 0, st>>>(W, ErrT, Hinv, N, C, 0, i1, (int)(i2 - i1), i2, C);

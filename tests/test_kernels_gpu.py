@@ -279,6 +279,21 @@ def test_gptq_fasterquant_with_reference_hinv(ops, golden_gptq):
             assert (Q - run["Q"]).abs().max().item() <= 2 * run["scale"].abs().max().item() + 1e-6
 
 
+def test_gptq_tensor_core_lazy_update_opt_in():
+    """B200WOQ_LAZY_TC=1 routes the lazy update through the tcgen05 3xTF32 kernel (gptq_tc.cu).  The switch is read once
+    per process, so the same kernel-level parity test is re-run in a child process; the bar is the multi-block bar."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, B200WOQ_LAZY_TC="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_kernels_gpu.py"), "-q", "-x", "-k",
+                        "test_gptq_fasterquant_with_reference_hinv or test_gptq_layer_pipeline_vs_reference"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:]
+
+
 def test_gptq_layer_pipeline_vs_reference(ops, golden_gptq):
     """End to end for one layer: Hessian kernel -> cuSOLVER inverse factor -> column loop -> codes."""
     W, X = golden_gptq["W"], golden_gptq["X"]
