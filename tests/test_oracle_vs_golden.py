@@ -106,3 +106,32 @@ def test_awq_stats_and_search(golden_awq):
     ratio, chist = O.awq_search_clip_module(g["W"], g["bias"], g["X"], 32, "asym")
     assert chist == g["clip_hist"]
     assert ratio == 1 - min(range(10), key=lambda i: g["clip_hist"][i]) / 100
+
+
+def test_oracle_reproduces_reference_rtn_option_matrix(golden_e2e, golden_options):
+    """Pins the oracle's RTN + pack restatement on the option surface: for every RTN case of the option matrix
+    (bits 2/3/4/8, per-channel, asym, full_range, mse_search, quantised lm_head) the oracle applied to the initial
+    weights must give exactly the packed tensors the live reference produced through its public API."""
+    init = golden_e2e["init_state"]
+    checked = 0
+    for tag, case in golden_options["cases"].items():
+        if case["algo"] != "rtn":
+            continue
+        kw = case["kw"]
+        bits = int(kw["dtype"].lstrip("int")) if "dtype" in kw else kw["bits"]
+        scheme = "sym" if kw["use_sym"] else "asym"
+        for key, ref in case["state"].items():
+            if not key.endswith(".qweight"):
+                continue
+            name = key[: -len(".qweight")]
+            W = init[name + ".weight"].float()
+            g = kw["group_size"]
+            quantile = O.rtn_search_clip(W, bits, g, scheme, kw.get("use_full_range", False)) if kw.get("use_mse_search") else 1.0
+            q, s, z = O.rtn_quantize(W, bits, g, scheme, quantile, kw.get("use_full_range", False))
+            geff = W.shape[1] if g == -1 else g
+            qw, qz, sc = O.pack_optimum(q, s, z, bits, geff)
+            assert torch.equal(qw, ref), (tag, key)
+            assert torch.equal(qz, case["state"][name + ".qzeros"]), (tag, name)
+            assert torch.equal(sc, case["state"][name + ".scales"]), (tag, name)
+            checked += 1
+    assert checked >= 8 * 14
