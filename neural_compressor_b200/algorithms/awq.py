@@ -20,14 +20,13 @@ with the reference's semantics (awq.py:96-128).
 """
 from __future__ import annotations
 
-import copy
 from functools import partial
 from typing import Dict, List
 
 import torch
 
 from .. import ops
-from ..utils import (current_device, fetch_module, get_block_prefix, get_model_device, logger, move_to_device,
+from ..utils import (current_device, fetch_module, get_block_prefix, logger, move_to_device,
                      set_module)
 from .base_algorithm import Quantizer
 from .modules import MulLinear

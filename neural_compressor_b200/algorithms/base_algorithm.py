@@ -1,5 +1,4 @@
 """Quantizer contract.  Reference: neural_compressor/torch/algorithms/base_algorithm.py:25-126."""
-import copy
 from abc import ABC, abstractmethod
 from typing import Any, Optional
 

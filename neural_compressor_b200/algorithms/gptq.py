@@ -15,7 +15,6 @@ export).  Everything numeric runs on the B200:
 """
 from __future__ import annotations
 
-import math
 import os
 import contextlib
 import time

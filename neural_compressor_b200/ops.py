@@ -7,8 +7,7 @@ is no CPU path and no fallback.
 from __future__ import annotations
 
 import math
-from ctypes import c_void_p
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 

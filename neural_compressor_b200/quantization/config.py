@@ -13,10 +13,9 @@ dict round trip); the tuning-grid expansion of list-valued parameters is out of 
 """
 from __future__ import annotations
 
-import inspect
 import re
 from collections import OrderedDict
-from typing import Callable, Dict, List, Optional, Tuple, Union
+from typing import List, Optional, Tuple
 
 import torch
 

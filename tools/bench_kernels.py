@@ -5,7 +5,6 @@
 import json
 import math
 import sys
-import time
 
 import torch
 
