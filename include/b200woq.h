@@ -151,6 +151,9 @@ int b200woq_hessian_accumulate(const void* X, int x_dtype, int64_t T, int64_t C,
 int b200woq_hessian_finalize(float* H, int64_t C, double nsamples, float percdamp, uint8_t* dead_mask,
                              float* scratch, void* stream);
 
+/* Workspace of b200woq_gptq_fasterquant: the transposed error block Err^T fp32 [blocksize, N].  When the process
+ * runs with B200WOQ_LAZY_TC=1 (opt-in tensor-core lazy update, gptq_tc.cu) it also holds the TF32 hi/lo splits of
+ * Err^T and of Hinv: + 2*blocksize*N + 2*C*C floats. */
 int64_t b200woq_gptq_workspace_bytes(int64_t N, int64_t C, int blocksize);
 
 /* GPTQ.fasterquant column loop (gptq.py:1250-1304) + Quantizer.find_params/quantize (:1501-1637,
@@ -162,7 +165,8 @@ int64_t b200woq_gptq_workspace_bytes(int64_t N, int64_t C, int blocksize);
  *   scale/zero fp32 [N,G], G = ceil(C/groupsize) (groupsize<=0 => 1 group = per-channel)
  *   losses fp32 [N] per-row sum of (w-q)^2/d^2/2 (gptq.py:1294,1303,1318) (may be NULL)
  * blocksize must be a multiple of groupsize (or groupsize<=0) -- the find_params "stale view"
- * semantics of blocksize > groupsize are reproduced.  flags bit0: mse search. */
+ * semantics of blocksize > groupsize are reproduced.  flags bit0: mse search.
+ * The lazy update W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:] (gptq.py:1304) runs as exact fp32 FFMA tiles by default. */
 int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8_t* dead_mask, int64_t N, int64_t C,
                              int blocksize, int groupsize, int bits, int sym, int flags, uint8_t* codes, float* Q,
                              float* scale, float* zero, float* losses, void* workspace,
