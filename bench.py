@@ -10,13 +10,17 @@ quantised weights (its outputs are the next block's inputs), packing.  `--steps 
              (inputs resident in HBM when the timed region starts)
     e2e    = the same, through the public prepare()/convert() engine with the block weights in pinned HOST
              memory: every step copies its block H2D and its packed result D2H inside the timed region
-    decode = Llama-2-7B INT4 decode tokens/s through the 224 packed linears (WeightOnlyLinear.forward, batch 1)
+    full_model_wall_s = ONE un-warmed prepare() -> run_fn(128 seqs) -> convert() of the whole 32-block model, host wall
+             clock (perf_counter), first block included -- what a user's first call on a fresh process costs
+    decode = Llama-2-7B INT4 decode tokens/s through the 224 packed linears of a convert()-ed model, called as
+             modules (B200WeightOnlyLinear.forward) under a CUDA graph, batch 1..64
     roofline         = the dominant calibration kernel (Hessian SYRK, tensor bound)
-    roofline_decode  = the dequant-GEMV (HBM bound)
-    cpu_baseline     = the oracle port (reference arithmetic on torch CPU ops) on a bounded sample, host cores
+    roofline_decode  = the dequant-GEMV at batch 1 (HBM bound)
+    cpu_baseline     = the UNMODIFIED reference's GPTQ class (vendored under oracle/_ref by oracle/build_ref.py;
+                       kind "reference") on a bounded sample, host cores; the oracle port only if the copy is absent
 
-`--impl reference` times the reference's CPU arithmetic (oracle port; the Python reference cannot travel to the
-GPU box) on the same config with all host threads, rank 0 only.
+`--impl reference` runs the unmodified reference's public prepare()/convert() on one full Llama-2-7B-shaped decoder
+block on the host cores (rank 0 only) and reports the same metric.
 """
 import argparse
 import json
@@ -35,6 +39,10 @@ sys.path.insert(0, ROOT)
 HIDDEN, INTER, LAYERS, HEADS, VOCAB = 4096, 11008, 32, 32, 32000
 N_SAMPLES, SEQ = 128, 2048
 TOKENS = N_SAMPLES * SEQ
+TINY = os.environ.get("B200WOQ_BENCH_TINY") == "1"  # tests only: checks the JSON contract of the CPU arm in seconds
+if TINY:
+    HIDDEN, INTER, HEADS, VOCAB, SEQ = 256, 512, 4, 512, 128
+    TOKENS = N_SAMPLES * SEQ
 LINEARS = [("q", HIDDEN, HIDDEN), ("k", HIDDEN, HIDDEN), ("v", HIDDEN, HIDDEN), ("o", HIDDEN, HIDDEN),
            ("gate", INTER, HIDDEN), ("up", INTER, HIDDEN), ("down", HIDDEN, INTER)]
 
@@ -136,8 +144,12 @@ def run_b200(args):
     lib = _lib.load()
     pk = peaks()
     W, K = args.warmup, args.steps
-    n_blocks_needed = min(LAYERS, (2 * (W + K) if args.e2e else (W + K)) + (1 if args.phases else 0))
-    log(f"building Llama-2-7B-shape model with {n_blocks_needed} of {LAYERS} blocks on {dev}")
+    wall = full_model_wall(dev, rank, world) if args.wall else None
+    # every step is one decoder block of identical shape, so the steady-state run simply builds as many blocks as it
+    # consumes: W warm-up + K timed + 1 for the phase breakdown + Ke for the host-resident (e2e) leg
+    Ke = max(1, min(K, 6)) if args.e2e else 0
+    n_blocks_needed = W + K + 1 + Ke
+    log(f"building Llama-2-7B-shape model with {n_blocks_needed} decoder blocks on {dev}")
     model = build_llama(dev, n_blocks_needed)
     log("model built")
 
@@ -219,26 +231,27 @@ def run_b200(args):
                         algorithmic="T*C*(C+128) flops per launch: the symmetric half of the reference's 2*T*C^2")
     ops.PROFILE_HOOK = None
 
-    phases = None
-    if args.phases and W + K < n_blocks_needed:
-        engine.profile = True
-        for k_ in engine.timing:
-            engine.timing[k_] = 0.0
-        with torch.no_grad():
-            engine.quantize_block(W + K)
-        engine.profile = False
-        phases = {k_: round(v_ * 1e3, 1) for k_, v_ in engine.timing.items()}
-        log(f"phase breakdown of one extra block (ms, with syncs): {phases}")
-        W += 1  # that block is consumed
+    # phase breakdown: one extra block with a device sync after every phase (so it is slower than a timed step)
+    engine.profile = True
+    for k_ in engine.timing:
+        engine.timing[k_] = 0.0
+    with torch.no_grad():
+        engine.quantize_block(W + K)
+    engine.profile = False
+    phases = {k_: round(v_ * 1e3, 1) for k_, v_ in engine.timing.items()}
+    log(f"phase breakdown of one extra block (ms, with syncs): {phases}")
 
     e2e = None
-    if args.e2e and W + K + K <= n_blocks_needed:
-        blk_bytes = sum(p_.numel() * p_.element_size() for p_ in engine.blocks_info["transformers"][W + K].parameters())
-        ms_e2e, _ = timed_blocks(W + K, K, host_resident=True)
-        log(f"e2e {K} blocks: {ms_e2e / K:.1f} ms/step")
-        d2h = sum(b_.numel() * b_.element_size() for b_ in engine.blocks_info["transformers"][W + K].buffers())
-        e2e = dict(value=round(TOKENS / (ms_e2e / K * LAYERS / 1000.0), 1), unit="calib tokens/s",
-                   h2d_bytes_per_step=blk_bytes, d2h_bytes_per_step=d2h, ms_per_step=round(ms_e2e / K, 2))
+    if Ke:
+        first = W + K + 1
+        blk_bytes = sum(p_.numel() * p_.element_size() for p_ in engine.blocks_info["transformers"][first].parameters())
+        ms_e2e, _ = timed_blocks(first, Ke, host_resident=True)
+        log(f"e2e {Ke} blocks: {ms_e2e / Ke:.1f} ms/step")
+        d2h = sum(b_.numel() * b_.element_size() for b_ in engine.blocks_info["transformers"][first].buffers())
+        e2e = dict(value=round(TOKENS / (ms_e2e / Ke * LAYERS / 1000.0), 1), unit="calib tokens/s",
+                   h2d_bytes_per_step=blk_bytes, d2h_bytes_per_step=d2h, ms_per_step=round(ms_e2e / Ke, 2), steps=Ke,
+                   how="same engine through prepare()/convert(); each step's decoder block starts in pinned HOST memory "
+                       "(H2D inside the timed region) and its packed result is copied back to the host (D2H)")
 
     out = dict(metric="Llama-2-7B GPTQ-INT4-g128 calibration throughput (whole model)", value=round(value, 1),
                unit="calib tokens/s", n_gpus=world, steps=K, warmup=W, ms_per_step=round(ms_step, 2),
@@ -249,6 +262,8 @@ def run_b200(args):
                            global_batch=N_SAMPLES, seq_len=SEQ, parallelism=f"calib-dp{world}",
                            l2="inputs >> L2 (2.1 GB activations, 0.4 GB weights per step)"),
                gpu_launches=int(launches), clocks=clocks, e2e=e2e, roofline=roofline, phases_ms=phases)
+    if wall is not None:
+        out.update(wall)
     if rank == 0 and args.decode:
         del model, engine
         torch.cuda.empty_cache()
@@ -263,84 +278,155 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def full_model_wall(dev, rank, world):
+    """One UN-WARMED whole-model run through the public API: prepare() -> run_fn over the calibration set -> convert(),
+    host wall clock, first block (library initialisation, first-launch overheads) included."""
+    import torch.distributed as dist
+
+    import neural_compressor_b200.quantization as Q
+    from neural_compressor_b200.algorithms.gptq import shard_range
+
+    log(f"[wall] building the full {LAYERS}-block model")
+    model = build_llama(dev, LAYERS)
+    lo, hi = shard_range(N_SAMPLES, rank, world)
+    ids = calib_ids(dev, lo, hi)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    stamps = []
+    t0 = time.perf_counter()
+    cfg = Q.GPTQConfig(bits=4, group_size=128, use_sym=True, act_order=False, block_size=128, percdamp=0.01)
+    model = Q.prepare(model, cfg)
+    with torch.no_grad():
+        for x in ids:
+            model(x)
+    torch.cuda.synchronize()
+    t_cal = time.perf_counter()
+
+    def cb(_idx):
+        torch.cuda.synchronize()
+        stamps.append(time.perf_counter())
+
+    model.quantizer.gptq_quantizer.block_callback = cb
+    model = Q.convert(model)
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    wall_s = t1 - t0
+    if world > 1:
+        t = torch.tensor([wall_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_s = t.item()
+    per_block = [b - a for a, b in zip([t_cal] + stamps[:-1], stamps)]
+    rest = sorted(per_block[1:])
+    res = dict(full_model_wall_s=round(wall_s, 2),
+               full_model_wall=dict(prepare_and_capture_s=round(t_cal - t0, 2), first_block_s=round(per_block[0], 2),
+                                    median_later_block_s=round(rest[len(rest) // 2], 3) if rest else None,
+                                    blocks=len(per_block), what="perf_counter around prepare() + 128-seq run_fn + convert() of "
+                                    "the 32-block model in a fresh process, nothing warmed up; max over ranks"))
+    log(f"[wall] whole model, un-warmed: {wall_s:.1f} s (first block {per_block[0]:.2f} s, later blocks "
+        f"{res['full_model_wall']['median_later_block_s']} s)")
+    del model, ids
+    torch.cuda.empty_cache()
+    return res
+
+
+DECODE_BATCHES = (1, 2, 4, 8, 16, 32, 64)
+
+
 def bench_decode(dev, pk):
-    """Llama-2-7B INT4 decode: one token through the 224 packed linears (7 per block x 32), CUDA graph, weights of
-    all 32 blocks distinct (3.36 GB >> L2)."""
-    from neural_compressor_b200 import ops
+    """Llama-2-7B INT4 decode through the MODULES of a convert()-ed model: RTN INT4 g128 via the public API, then one
+    token (batch M) through the 224 `B200WeightOnlyLinear.forward` calls in model order under a CUDA graph.  The 32
+    blocks hold distinct weights (3.36 GB >> L2).  Also reported: the whole HF forward `model(ids)` (norms, rotary,
+    attention, lm_head included) for context."""
+    import neural_compressor_b200.quantization as Q
+    from neural_compressor_b200.algorithms.modules import B200WeightOnlyLinear
 
-    packs = []
-    g = torch.Generator().manual_seed(3)
-    base = {}
-    for name, N, Kd in LINEARS:
-        Wt = (torch.randn(N, Kd, generator=g) * 0.02).to(dev)
-        r = ops.rtn_quant_pack(Wt, 4, 128, True)
-        base[name] = (r["qweight"], r["qzeros"], r["scales"], ops.build_stream_layout(r["qweight"], r["qzeros"], r["scales"],
-                                                                                         4, 128, Kd, N))
-    for _ in range(LAYERS):
-        blk = {k: tuple(t.clone() for t in v) for k, v in base.items()}
-        # what modules.SiblingGroup builds for q/k/v and gate/up: the members' strip-major layouts, concatenated
-        blk["qkv"] = torch.cat([blk[n][3] for n in ("q", "k", "v")])
-        blk["gateup"] = torch.cat([blk[n][3] for n in ("gate", "up")])
-        packs.append(blk)
-    xh = torch.randn(1, HIDDEN, device=dev, dtype=torch.float16)
-    yh = {n: torch.empty(1, N, device=dev, dtype=torch.float16) for n, N, _ in LINEARS}
-    yh["qkv"] = torch.empty(1, 3 * HIDDEN, device=dev, dtype=torch.float16)
-    yh["gateup"] = torch.empty(1, 2 * INTER, device=dev, dtype=torch.float16)
+    model = build_llama(dev, LAYERS)
+    model = Q.convert(Q.prepare(model, Q.RTNConfig(bits=4, group_size=128, use_sym=True, use_layer_wise=False)))
+    torch.cuda.synchronize()
+    layers = model.model.layers
+    assert isinstance(layers[0].self_attn.q_proj, B200WeightOnlyLinear)
+    by_w = sum(N * Kd // 2 + 2 * N * Kd // 128 + N * Kd // 256 for _, N, Kd in LINEARS) * LAYERS
 
-    def token_fused(flags):
-        x = xh
-        for blk in packs:
-            ops.woq_linear_stream(x, blk["qkv"], None, 4, 128, HIDDEN, 3 * HIDDEN, out_dtype=torch.float16, flags=flags,
-                                  out=yh["qkv"])
-            ops.woq_linear_stream(x, blk["o"][3], None, 4, 128, HIDDEN, HIDDEN, out_dtype=torch.float16, flags=flags,
-                                  out=yh["o"])
-            ops.woq_linear_stream(x, blk["gateup"], None, 4, 128, HIDDEN, 2 * INTER, out_dtype=torch.float16, flags=flags,
-                                  out=yh["gateup"])
-            ops.woq_linear_stream(yh["gateup"][:, :INTER], blk["down"][3], None, 4, 128, INTER, HIDDEN,
-                                  out_dtype=torch.float16, flags=flags, out=yh["down"])
-            x = yh["down"]
+    def chain(x, xi):
+        for lyr in layers:
+            a, m = lyr.self_attn, lyr.mlp
+            a.q_proj(x), a.k_proj(x), a.v_proj(x)
+            a.o_proj(x)
+            m.gate_proj(x), m.up_proj(x)
+            x = m.down_proj(xi)
+        return x
 
-    def token(flags, use_stream):
-        x = xh
-        for blk in packs:
-            for name, N, Kd in LINEARS:
-                inp = x if Kd == HIDDEN else yh["up"]
-                qw, qz, sc, lay = blk[name]
-                if use_stream:
-                    ops.woq_linear_stream(inp, lay, None, 4, 128, Kd, N, out_dtype=torch.float16, flags=flags, out=yh[name])
-                else:
-                    ops.woq_linear(inp, qw, qz, sc, None, 4, 128, Kd, N, out_dtype=torch.float16, flags=flags, out=yh[name])
-            x = yh["down"]
-
-    res = {}
-    by = sum(N * Kd // 2 + 2 * N * Kd // 128 + N * Kd // 256 + 2 * Kd + 2 * N for _, N, Kd in LINEARS) * LAYERS
-    for flags, use_stream, tag in ((0, False, "optimum_layout"), (2, False, "optimum_layout_pdl"),
-                                   (0, True, "stream_layout"), (2, True, "stream_layout_pdl"),
-                                   (2, None, "stream_layout_pdl_siblings_fused")):
-        run = (lambda: token_fused(flags)) if use_stream is None else (lambda: token(flags, use_stream))
-        run()
+    def timed_graph(fn, reps=20):
+        fn()
+        fn()
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            run()
+            fn()
         for _ in range(3):
             graph.replay()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         s.record()
-        for _ in range(20):
+        for _ in range(reps):
             graph.replay()
         e.record()
         torch.cuda.synchronize()
-        ms = s.elapsed_time(e) / 20
-        res[tag] = dict(ms_per_token=round(ms, 4), tokens_per_s=round(1000.0 / ms, 1), GBs=round(by / ms / 1e6, 1))
-    best = max(res.values(), key=lambda r: r["tokens_per_s"])
-    return dict(decode=dict(metric="Llama-2-7B INT4 decode tokens/s (224 WOQ linears, batch 1, CUDA graph)", **best,
-                            variants=res, bytes_per_token=by, dequant_gemm_tflops=round(
-                                2 * sum(N * Kd for _, N, Kd in LINEARS) * LAYERS / (best["ms_per_token"] * 1e9), 2)),
-                roofline_decode=dict(bound="hbm", kernel="woq_gemm_stream_kernel / woq_gemm_mma_kernel (best variant)", achieved=best["GBs"],
-                                     peak=pk["hbm_gbs"], unit="GB/s", frac=round(best["GBs"] / pk["hbm_gbs"], 4),
-                                     traffic=None, peak_source=pk["source"]))
+        return s.elapsed_time(e) / reps
+
+    per_m = {}
+    for M in DECODE_BATCHES:
+        x = torch.randn(M, 1, HIDDEN, device=dev, dtype=torch.float16)
+        xi = torch.randn(M, 1, INTER, device=dev, dtype=torch.float16)
+        with torch.no_grad():
+            ms = timed_graph(lambda: chain(x, xi))
+        by = by_w + sum(2 * M * Kd + 2 * M * N for _, N, Kd in LINEARS) * LAYERS
+        fl = 2 * M * sum(N * Kd for _, N, Kd in LINEARS) * LAYERS
+        per_m[str(M)] = dict(ms_per_step=round(ms, 4), tokens_per_s=round(1000.0 * M / ms, 1), GBs=round(by / ms / 1e6, 1),
+                             hbm_frac=round(by / ms / 1e6 / pk["hbm_gbs"], 4), dequant_gemm_tflops=round(fl / ms / 1e9, 2))
+        log(f"decode M={M}: {ms:.3f} ms, {per_m[str(M)]['GBs']} GB/s ({per_m[str(M)]['hbm_frac']:.1%} of HBM)")
+    # whole HF forward, batch 1 (context only: ~300 small eager kernels and a 262 MB fp16 lm_head ride along)
+    whole = None
+    try:
+        ids = torch.randint(0, VOCAB, (1, 1), device=dev)
+        with torch.no_grad():
+            ms = timed_graph(lambda: model(ids).logits, reps=10)
+        whole = dict(ms_per_token=round(ms, 4), tokens_per_s=round(1000.0 / ms, 1))
+    except Exception as ex:  # graph capture of the HF forward is best effort
+        whole = dict(error=f"{type(ex).__name__}: {str(ex)[:200]}")
+        torch.cuda.synchronize()
+    packed = sum(b.numel() * b.element_size() for m_ in model.modules() if isinstance(m_, B200WeightOnlyLinear)
+                 for n_, b in m_.named_buffers(recurse=False))
+    derived = 0
+    seen = set()
+    for m_ in model.modules():
+        for holder in (m_, getattr(m_, "_siblings", None)):
+            t = getattr(holder, "layout", None) if holder is not m_ else getattr(m_, "_stream", None)
+            if isinstance(t, torch.Tensor) and t.untyped_storage().data_ptr() not in seen:
+                seen.add(t.untyped_storage().data_ptr())
+                derived += t.untyped_storage().nbytes()
+    b1 = per_m["1"]
+    del model
+    torch.cuda.empty_cache()
+    return dict(decode=dict(metric="Llama-2-7B INT4 decode tokens/s (224 WOQ linears called as modules of a convert()-ed "
+                                   "model, CUDA graph)", ms_per_token=b1["ms_per_step"], tokens_per_s=b1["tokens_per_s"],
+                            GBs=b1["GBs"], by_batch=per_m, bytes_per_token_batch1=by_w + sum(2 * Kd + 2 * N for _, N, Kd in LINEARS) * LAYERS,
+                            model_forward_batch1=whole, packed_bytes=packed, derived_layout_bytes=derived,
+                            memory_overhead=round(derived / max(packed, 1), 3)),
+                roofline_decode=dict(bound="hbm", kernel="dequant-GEMV, batch 1 (B200WeightOnlyLinear.forward)",
+                                     achieved=b1["GBs"], peak=pk["hbm_gbs"], unit="GB/s", frac=b1["hbm_frac"],
+                                     traffic=decode_traffic_per_token(), peak_source=pk["source"]))
+
+
+def decode_traffic_per_token():
+    """DRAM bytes per decoded token from the newest committed ncu capture (profiles/rNN_decode_traffic.json)."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_decode_traffic.json")))
+    if not files:
+        return None
+    return json.load(open(files[-1])).get("dram_bytes_per_token")
 
 
 def syrk_traffic_per_launch(flops_per_launch):
@@ -360,48 +446,120 @@ def syrk_traffic_per_launch(flops_per_launch):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
+def _reference_or_none():
+    """The unmodified reference, imported from oracle/_ref (vendored by oracle/build_ref.py); None when absent."""
+    try:
+        from oracle import ref_loader
+
+        if not (ref_loader.vendored_available() or ref_loader.reference_available()):
+            return None
+        ref_loader.load_reference()
+        from neural_compressor.torch.algorithms.weight_only import gptq as ref_gptq
+
+        return ref_gptq
+    except Exception as ex:  # pragma: no cover
+        log(f"reference import failed ({type(ex).__name__}: {ex}); falling back to the oracle port")
+        return None
+
+
 def cpu_baseline(sample_layers=1):
-    """The reference's CPU arithmetic (oracle port) on a bounded sample: GPTQ.add_batch for one 2048-token sequence
-    at C=4096 and C=11008, GPTQ.fasterquant on one [4096,4096] layer, pack; extrapolated to the whole model with
-    the reference's own structure (7 Hessians per block per sample) -- forwards NOT counted."""
+    """The reference's CPU arithmetic on a bounded sample: GPTQ.add_batch for one 2048-token sequence at C=4096 and
+    C=11008, GPTQ.fasterquant on one [4096,4096] layer, export + pack; extrapolated to the whole model with the
+    reference's own structure (7 Hessians per block per sample) -- forwards NOT counted.  Uses the
+    UNMODIFIED reference classes when oracle/_ref is present (kind "reference"), else the oracle port (kind "port")."""
+    ref = _reference_or_none()
     from oracle import woq_oracle as O
 
     cores = os.cpu_count()
     torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(0)
+    qcfg = dict(dtype="int", bits=4, sym=True, group_size=128, mse=False, perchannel=True, use_double_quant=False,
+                double_quant_sym=False)
+
+    def layer(N, C):
+        if ref is None:
+            return O.GPTQLayerOracle(N, C, bits=4, sym=True)
+        lin = torch.nn.Linear(C, N, bias=False)
+        gp = ref.GPTQ(lin, lin.weight.data, "cpu")
+        gp.quantizer.configure(dict(qcfg))
+        return gp
+
+    def add(lay, x):
+        lay.add_batch(x) if ref is None else lay.add_batch(x, None)
+
     t_add = {}
     for C in (HIDDEN, INTER):
-        lay = O.GPTQLayerOracle(8, C, bits=4, sym=True)
+        lay = layer(8, C)
         x = torch.randn(1, SEQ, C, generator=g)
-        lay.add_batch(x)  # warm
+        add(lay, x)  # warm
         t0 = time.perf_counter()
-        lay.add_batch(x)
+        add(lay, x)
         t_add[C] = time.perf_counter() - t0
     # column loop: thousands of tiny torch ops -- it does not scale past ~16 threads (more threads only add
     # fork/join overhead), so cap it there; add_batch above used every core
     fq_threads = min(cores, 16)
     torch.set_num_threads(fq_threads)
-    lay = O.GPTQLayerOracle(HIDDEN, HIDDEN, bits=4, sym=True)
+    lay = layer(HIDDEN, HIDDEN)
     for _ in range(3):
-        lay.add_batch(torch.randn(1, SEQ, HIDDEN, generator=g))
+        add(lay, torch.randn(1, SEQ, HIDDEN, generator=g))
     Wt = torch.randn(HIDDEN, HIDDEN, generator=g) * 0.02
     t0 = time.perf_counter()
-    r = lay.fasterquant(Wt, blocksize=128, percdamp=0.01, groupsize=128)
+    if ref is None:
+        r = lay.fasterquant(Wt, blocksize=128, percdamp=0.01, groupsize=128)
+        scale, zero, Qf = r["scale"], r["zero"], r["Q"]
+    else:
+        scale, _, zero, Qf = lay.fasterquant(Wt, blocksize=128, percdamp=0.01, groupsize=128)
     t_fq = time.perf_counter() - t0
     t0 = time.perf_counter()
-    codes = O.GPTQLayerOracle.export_codes(r["Q"], r["scale"], r["zero"], 128, True)
-    O.pack_optimum(codes, r["scale"], None, 4, 128)
+    if ref is None:
+        codes = O.GPTQLayerOracle.export_codes(Qf, scale, zero, 128, True)
+        O.pack_optimum(codes, scale, None, 4, 128)
+    else:
+        from neural_compressor.torch.algorithms.weight_only.modules import INCWeightOnlyLinear
+        from neural_compressor.torch.algorithms.weight_only.utility import quant_weight_w_scale
+
+        codes = quant_weight_w_scale(Qf, scale, None, None, 128, dtype="int").type(torch.int32)  # gptq.py:796-813
+        mod = INCWeightOnlyLinear(HIDDEN, HIDDEN, dtype="int", bits=4, group_size=128, zp=False, bias=False,
+                                  use_optimum_format=True, device="cpu")
+        mod.pack(codes, scale, None, None)  # gptq.py:838
     t_pack = time.perf_counter() - t0
     torch.set_num_threads(cores)
     fq_units = sum(N * Kd * Kd for _, N, Kd in LINEARS) / (HIDDEN**3)
     per_block = N_SAMPLES * (6 * t_add[HIDDEN] + t_add[INTER]) + t_fq * fq_units + t_pack * (sum(N * Kd for _, N, Kd in LINEARS) / HIDDEN**2)
     total = per_block * LAYERS
-    return dict(value=round(TOKENS / total, 3), unit="calib tokens/s", cores=cores, kind="port",
+    return dict(value=round(TOKENS / total, 3), unit="calib tokens/s", cores=cores, kind="port" if ref is None else "reference",
                 fasterquant_threads=fq_threads,
-                sample=f"add_batch 1x{SEQ} tokens @C=4096 ({t_add[HIDDEN]:.3f}s) and @C=11008 ({t_add[INTER]:.3f}s), "
-                       f"fasterquant+export+pack of one 4096x4096 layer ({t_fq:.2f}s+{t_pack:.2f}s); extrapolated x128 "
+                sample=f"{'oracle port' if ref is None else 'unmodified reference classes (oracle/_ref)'}: GPTQ.add_batch 1x{SEQ} "
+                       f"tokens @C=4096 ({t_add[HIDDEN]:.3f}s) and @C=11008 ({t_add[INTER]:.3f}s), GPTQ.fasterquant + "
+                       f"quant_weight_w_scale + pack of one 4096x4096 layer ({t_fq:.2f}s+{t_pack:.2f}s); extrapolated x128 "
                        f"samples x 7 Hessians x 32 blocks, fasterquant scaled by N*C^2, block forwards not counted",
                 est_full_model_sec=round(total, 1))
+
+
+def reference_block_run(n_seqs):
+    """The UNMODIFIED reference through its own public API -- prepare(GPTQConfig) / run_fn / convert() -- on a
+    Llama-2-7B-shaped model with ONE decoder block (fp32 on the CPU, `INC_TARGET_DEVICE=cpu`), `n_seqs` calibration
+    sequences of 2048 tokens.  Returns the wall seconds of prepare + run_fn + convert."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from neural_compressor.torch.quantization import GPTQConfig, convert, prepare
+
+    cfg = LlamaConfig(hidden_size=HIDDEN, intermediate_size=INTER, num_hidden_layers=1, num_attention_heads=HEADS,
+                      num_key_value_heads=HEADS, vocab_size=VOCAB, max_position_embeddings=4096, tie_word_embeddings=False)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).eval()
+    model.config.use_cache = False
+    g = torch.Generator().manual_seed(1234)
+    ids = [torch.randint(0, VOCAB, (1, SEQ), generator=g) for _ in range(n_seqs)]
+    t0 = time.perf_counter()
+    qc = GPTQConfig(bits=4, group_size=128, use_sym=True, act_order=False, block_size=128, percdamp=0.01,
+                    model_path=ROOT)  # model_path: any existing directory (layer_wise/utils.py:190-196)
+    model = prepare(model, qc)
+    with torch.no_grad():
+        for x in ids:
+            model(x)
+    model = convert(model)
+    return time.perf_counter() - t0
 
 
 def run_reference(args):
@@ -409,16 +567,38 @@ def run_reference(args):
     if rank != 0:
         return
     t0 = time.perf_counter()
-    vals = []
-    for _ in range(max(1, min(args.steps, 2))):  # each step is the bounded sample; a few repeats at most
-        vals.append(cpu_baseline())
-    b = max(vals, key=lambda v: v["value"])
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    ref = _reference_or_none()
+    if ref is None:
+        b = cpu_baseline()
+        timed = None
+    else:
+        # one full decoder block, timed end to end twice (s1 and s2 calibration sequences): the per-sequence cost
+        # (7 Hessian updates + 2 block forwards) and the per-block cost (7 x fasterquant, export, pack) separate
+        # exactly, and the 128-sequence block time follows without guessing either
+        s1, s2 = [int(v) for v in os.environ.get("B200WOQ_REF_SEQS", "1,3").split(",")]
+        t1 = reference_block_run(s1)
+        log(f"reference block with {s1} seqs: {t1:.1f} s")
+        t2 = reference_block_run(s2)
+        log(f"reference block with {s2} seqs: {t2:.1f} s")
+        per_seq = max((t2 - t1) / (s2 - s1), 0.0)
+        fixed = max(t1 - s1 * per_seq, 0.0)
+        blk = fixed + N_SAMPLES * per_seq
+        timed = {f"block_{s1}_seqs_s": round(t1, 2), f"block_{s2}_seqs_s": round(t2, 2), "per_seq_s": round(per_seq, 3),
+                 "per_block_fixed_s": round(fixed, 2), "block_128_seqs_s": round(blk, 1)}
+        b = dict(value=round(TOKENS / (blk * LAYERS), 3), unit="calib tokens/s", cores=cores, kind="reference",
+                 sample=f"unmodified reference (oracle/_ref) prepare/run_fn/convert of ONE full Llama-2-7B decoder block, fp32 "
+                        f"on the host, timed with {s1} and with {s2} sequences of {SEQ} tokens; per-sequence and per-block "
+                        f"costs separated linearly, 128 sequences x 32 blocks follows",
+                 est_full_model_sec=round(blk * LAYERS, 1), timed=timed)
     out = dict(impl="reference", metric="Llama-2-7B GPTQ-INT4-g128 calibration throughput (whole model)",
                value=b["value"], unit="calib tokens/s", n_gpus=int(os.environ.get("WORLD_SIZE", "1")), steps=args.steps,
                warmup=args.warmup, ms_per_step=round(b["est_full_model_sec"] * 1000 / LAYERS, 1), higher_is_better=True,
                scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-               config=dict(workload="GPTQ INT4 g128 sym block_size=128, Llama-2-7B shapes, 128x2048 calib tokens; "
-                                    "CPU arithmetic of the reference on a bounded sample, extrapolated"),
+               config=dict(workload="GPTQ INT4 g128 sym block_size=128 percdamp=.01, Llama-2-7B shapes, 128x2048 calib tokens; "
+                                    "step = one decoder block of the 32 (CPU: timed on a bounded number of sequences)"
+                                    + (" [B200WOQ_BENCH_TINY test shapes, not a measurement]" if TINY else "")),
                cpu_baseline=b, e2e=dict(value=b["value"], unit="calib tokens/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                gpu_launches=0, wall_s=round(time.perf_counter() - t0, 1))
     print(json.dumps(out))
@@ -431,7 +611,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", dest="e2e", action="store_false")
-    ap.add_argument("--phases", action="store_true", help="also report a per-phase breakdown of one extra block")
+    ap.add_argument("--no-wall", dest="wall", action="store_false",
+                    help="skip the un-warmed whole-model prepare/run_fn/convert wall-clock run")
     ap.add_argument("--no-decode", dest="decode", action="store_false")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     a = ap.parse_args()

@@ -322,8 +322,11 @@ class RAWGPTQuantizer:
         blocks = self.blocks_info["transformers"]
         for p in self.model.parameters():
             p.requires_grad = False
+        cb = getattr(self, "block_callback", None)  # optional progress hook: called with the index of each finished block
         for block_idx in range(len(blocks)):
             self.quantize_block(block_idx)
+            if cb is not None:
+                cb(block_idx)
         return self.model
 
     @torch.no_grad()

@@ -86,6 +86,20 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
         else:
             self.g_idx = None
 
+    # the packed tensors have FIXED storage dtypes (they are an on-disk contract and the kernels reinterpret raw
+    # pointers): `model.to(torch.bfloat16)` / `.half()` / `.float()` must move them between devices but never re-type
+    # `scales` (fp16), `bias` (fp16) or `scale_bf16_to_fp8` (bf16) -- a bf16 round trip would also destroy scale bits
+    _FIXED_DTYPE = ("scales", "bias", "scale_bf16_to_fp8")
+
+    def _apply(self, fn, recurse=True):
+        keep = {n: self._buffers[n] for n in self._FIXED_DTYPE if isinstance(self._buffers.get(n), torch.Tensor)}
+        super()._apply(fn, recurse)
+        for n, old in keep.items():
+            new = self._buffers[n]
+            if new.dtype != old.dtype:
+                self._buffers[n] = old.to(new.device)
+        return self
+
     # ------------------------------------------------------------------ pack
     def pack(self, int_weight, scales, zp, bias, scale_bf16_to_fp8=None, g_idx=None, **kwargs):
         """modules.py:321-375.  int_weight [N,K] integer-valued (sym: in [-2^(b-1), 2^(b-1)-1], zp None);
@@ -156,7 +170,11 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
     def forward(self, input, input_scale=None):
         out_dtype = input.dtype if input.dtype in (torch.float16, torch.bfloat16) else torch.float32
         rows = input.numel() // self.in_features
-        if (rows <= STREAM_MAX_ROWS and self.bits == 4 and self.g_idx is None and self.qweight.is_cuda
+        # The small-batch tensor-core kernels stage the activations as fp16 (the reference itself casts the input to the
+        # fp16 weight's dtype on an accelerator, modules.py:606).  bf16 / fp32 activations can exceed 65504, so they take
+        # the fp32-math kernel (rows <= 8) or recover() + a library GEMM in the input dtype, like the reference's CPU path.
+        fp16_in = input.dtype == torch.float16
+        if (rows <= STREAM_MAX_ROWS and fp16_in and self.bits == 4 and self.g_idx is None and self.qweight.is_cuda
                 and os.environ.get("B200WOQ_STREAM", "1") != "0"):
             group = getattr(self, "_siblings", None)
             if group is not None and rows == 1 and input_scale is None:
@@ -166,7 +184,7 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
                 return ops.woq_linear_stream(input, layout, self.bias, self.bits, self.group_size, self.in_features,
                                              self.out_features, input_scale=input_scale, out_dtype=out_dtype,
                                              flags=self._stream_flags())
-        if rows > GEMM_MAX_ROWS:
+        if rows > GEMM_MAX_ROWS or (not fp16_in and rows > 8):
             # prefill / calibration batches are compute-bound: recover the fp16 weight once (K4 dequantize kernel) and
             # run a plain library GEMM in the input's dtype -- literally the reference's forward (modules.py:594-610:
             # recover() then F.linear), so calibration forwards through already-packed modules keep fp32 activations
@@ -175,7 +193,7 @@ class B200WeightOnlyLinear(WeightOnlyLinear):
             return torch.nn.functional.linear(x, w, None if self.bias is None else self.bias.to(input.dtype))
         return ops.woq_linear(input, self.qweight, self.qzeros, self.scales, self.bias, self.bits, self.group_size,
                               self.in_features, self.out_features, g_idx=self.g_idx, input_scale=input_scale,
-                              out_dtype=out_dtype)
+                              out_dtype=out_dtype, flags=0 if fp16_in else 1)  # bit 0: general fp32-math kernel
 
 
 class SiblingGroup:

@@ -108,4 +108,8 @@ class RTNQuantizer(Quantizer):
             if name == "":
                 return new_module
             set_module(model, name, new_module)
+        if model_device.type != "cuda":
+            # packed modules only exist on the B200 (no CPU path): keep the rest of the model with them, as the AWQ
+            # and GPTQ quantizers do, instead of returning a mixed-device model that fails at its first forward
+            model = model.to(device)
         return model

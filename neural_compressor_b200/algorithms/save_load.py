@@ -167,30 +167,46 @@ def load(model_name_or_path, original_model=None, format="default", device="cuda
         qcfg = json.load(f)
     state = torch.load(os.path.join(model_name_or_path, WEIGHT_NAME), map_location=device)
     model = original_model.to(device)
+    # Which modules are packed is decided by the checkpoint (`<name>.qweight` present), not by the qconfig dtype: the
+    # GPTQ engine mirrors the reference's `get_layer_config` fallback (gptq.py:367-382), which quantises in-block
+    # layers even when their own entry says fp32, so the tensors are the ground truth.
+    first_cfg = None
+    for body in qcfg.values():
+        (_algo, c), = body.items()
+        if c.get("dtype") != "fp32":
+            first_cfg = c
+            break
     for key, body in qcfg.items():
         op_name = key.split("'")[1]
         (algo, cfg), = body.items()
-        if cfg.get("dtype") == "fp32":
-            continue
         packed_name = op_name + ".qweight"
         wrapped = op_name + ".linear.qweight"
         if packed_name not in state and wrapped not in state:
             continue
+        if cfg.get("dtype") == "fp32":
+            assert first_cfg is not None, f"{op_name}: packed tensors in the checkpoint but no quantised config entry"
+            cfg = first_cfg
         m = fetch_module(model, op_name)
         lin = m
         in_f = lin.in_features if hasattr(lin, "in_features") else lin.weight.shape[0]
         out_f = lin.out_features if hasattr(lin, "out_features") else lin.weight.shape[1]
         prefix = op_name + (".linear" if wrapped in state else "")
         bits = cfg["bits"]
+        if isinstance(cfg.get("dtype"), str) and cfg["dtype"] != "int" and cfg["dtype"].startswith("int"):
+            bits = int(cfg["dtype"].lstrip("int"))
         g = state[prefix + ".scales"].shape[0]
         group_size = cfg["group_size"] if cfg["group_size"] > 0 else in_f
         new = B200WeightOnlyLinear(in_f, out_f, dtype="int", bits=bits, group_size=group_size,
                                    zp=True, bias=True, g_idx=(prefix + ".g_idx") in state, device=device)
-        assert new.scales.shape[0] == g
+        assert new.scales.shape[0] == g, f"{op_name}: {new.scales.shape[0]} groups expected, checkpoint has {g}"
         if wrapped in state:
             new = MulLinear(new, torch.empty(in_f, device=device))
         set_module(model, op_name, new)
-    model.load_state_dict(state, strict=False)
+    result = model.load_state_dict(state, strict=False)
+    stray = [k for k in result.unexpected_keys if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales", "g_idx")]
+    if stray or result.missing_keys:
+        raise RuntimeError(f"quantized checkpoint does not match the rebuilt model: unexpected packed tensors {stray[:8]}, "
+                           f"missing {list(result.missing_keys)[:8]}")
     from .modules import fuse_sibling_linears
 
     fuse_sibling_linears(model)

@@ -481,11 +481,8 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
     for (int64_t c0 = i1; c0 < i2; c0 += SUB) {
       const int ncols = (int)std::min<int64_t>(SUB, i2 - c0);
       const size_t smem = ((size_t)SUB * SUB + 4 * SUB) * sizeof(float);
-      static bool attr_set = false;
-      if (!attr_set) {
-        WOQ_CUDA(cudaFuncSetAttribute(gptq_subblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-      }
+      // per-device attribute: set on every call (cheap), never cached per process
+      WOQ_CUDA(cudaFuncSetAttribute(gptq_subblock_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       gptq_subblock_kernel<<<(unsigned)ceil_div(N, rows_per_cta), 32 * SUB_WARPS, smem, st>>>(
           W, Hinv, N, C, c0, ncols, per_channel ? 0 : g, G, maxq, scale, zero, codes, Q, ErrT, c0 - i1, losses, ErrT_hi,
           ErrT_lo);

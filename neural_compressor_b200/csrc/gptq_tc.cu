@@ -311,11 +311,8 @@ int lazy_tc_make_plan(LazyTcPlan* plan, const float* e_hi, const float* e_lo, in
 int lazy_tc_update(const LazyTcPlan* plan, float* W, int64_t N, int64_t C, int64_t e0, int64_t r0, int KK, int64_t j0,
                    int64_t j1, cudaStream_t st) {
   using namespace lazytc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    WOQ_CUDA(cudaFuncSetAttribute(gptq_lazy_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // per-device attribute: set on every call (cheap), never cached per process
+  WOQ_CUDA(cudaFuncSetAttribute(gptq_lazy_update_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   const int n_row_tiles = (int)ceil_div(N, TM), n_col_tiles = (int)ceil_div(j1 - j0, TN);
   const int64_t tiles = (int64_t)n_row_tiles * n_col_tiles;
   // D = f32, A/B = TF32, both MN-major, N = 128, M = 128 (cute/arch/mma_sm100_desc.hpp: InstrDescriptor)

@@ -467,11 +467,8 @@ int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C,
   const uint32_t fmt = (x_dtype == B200WOQ_F16) ? 0u : 1u;
   const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(TN >> 3) << 17) |
                          ((uint32_t)(TM >> 4) << 24);
-  static bool attr_set = false;
-  if (!attr_set) {
-    WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // per-device attribute: set on every call (cheap), never cached per process
+  WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   static const int pair_mode = getenv("B200WOQ_SYRK_PAIR") ? atoi(getenv("B200WOQ_SYRK_PAIR")) : kPairDefault;
   if (pair_mode) {
     static const int super_rows2 =
@@ -479,11 +476,8 @@ int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C,
     // cta_group::2: M = 256 (128 rows per CTA), N = 256
     const uint32_t idesc2 = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
                             ((uint32_t)(256 >> 4) << 24);
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
-      attr2_set = true;
-    }
+    // per-device attribute: set on every call (cheap), never cached per process
+    WOQ_CUDA(cudaFuncSetAttribute(hessian_syrk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_BYTES));
     const int nt = (int)ceil_div(C, 256);
     unsigned tiles = 0;
     for (int ti0 = 0; ti0 < nt; ti0 += super_rows2) tiles += (unsigned)(std::min(super_rows2, nt - ti0) * (nt - ti0));

@@ -93,6 +93,8 @@ def pack_codes(codes: torch.Tensor, bits: int):
 
 def unpack(qweight, qzeros, bits, in_features, out_features, n_groups):
     require_cuda(qweight, "qweight")
+    if qweight.dtype != torch.int32 or qzeros.dtype != torch.int32:
+        raise _lib.B200WOQError("qweight / qzeros must be int32")
     codes = torch.empty((out_features, in_features), dtype=torch.uint8, device=qweight.device)
     zps = torch.empty((out_features, n_groups), dtype=torch.uint8, device=qweight.device)
     check(_lib.load().b200woq_unpack(ptr(qweight), ptr(qzeros), out_features, in_features, n_groups, bits, ptr(codes),
@@ -103,6 +105,7 @@ def unpack(qweight, qzeros, bits, in_features, out_features, n_groups):
 def dequantize(qweight, qzeros, scales, bits, group_size, in_features, out_features, g_idx=None):
     """recover(): fp16 [N,K] (modules.py:413-443)."""
     require_cuda(qweight, "qweight")
+    _check_packed(qweight, qzeros, scales, bits, in_features, out_features, g_idx)
     out = torch.empty((out_features, in_features), dtype=torch.float16, device=qweight.device)
     check(_lib.load().b200woq_dequantize(ptr(qweight), ptr(qzeros), ptr(scales), ptr(g_idx), out_features, in_features,
                                          bits, group_size, ptr(out), stream_ptr(qweight.device)), "dequantize")
@@ -111,6 +114,36 @@ def dequantize(qweight, qzeros, scales, bits, group_size, in_features, out_featu
 
 # ------------------------------------------------------------------ K6: fused dequant GEMM
 _WS_CACHE = {}
+
+
+def _check_packed(qweight, qzeros, scales, bits, in_features, out_features, g_idx=None, input_scale=None, bias=None):
+    """The kernels reinterpret raw pointers: a `model.to(torch.bfloat16)` that silently re-typed `scales`, a float
+    `g_idx` or a mis-shaped tensor would decode garbage without any error, so every entry validates dtype, shape, device
+    and contiguity of the packed tensors first."""
+    np_ = n_pack(bits)
+
+    def need(t, name, dtype, shape=None):
+        if t is None:
+            return
+        if not t.is_cuda:
+            raise _lib.B200WOQError(f"{name} must be a CUDA tensor (neural_compressor_b200 has no CPU path)")
+        if t.dtype != dtype:
+            raise _lib.B200WOQError(f"{name} must be {dtype}, got {t.dtype} (was the packed module cast with .to(dtype)?)")
+        if not t.is_contiguous():
+            raise _lib.B200WOQError(f"{name} must be contiguous")
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise _lib.B200WOQError(f"{name} must have shape {tuple(shape)}, got {tuple(t.shape)}")
+
+    need(qweight, "qweight", torch.int32, (math.ceil(in_features / np_), out_features))
+    G = scales.shape[0] if scales is not None and scales.dim() == 2 else -1
+    need(scales, "scales", torch.float16, (G, out_features))
+    need(qzeros, "qzeros", torch.int32, (G, math.ceil(out_features / np_)))
+    need(g_idx, "g_idx", torch.int32, (in_features,))
+    need(input_scale, "input_scale", torch.float32, (in_features,))
+    if bias is not None:
+        if bias.dtype not in _lib._DT:
+            raise _lib.B200WOQError(f"bias dtype {bias.dtype} unsupported")
+        need(bias, "bias", bias.dtype, (out_features,))
 
 
 def _workspace(device, nbytes: int) -> torch.Tensor:
@@ -126,6 +159,7 @@ def woq_linear(x, qweight, qzeros, scales, bias, bits, group_size, in_features, 
                input_scale=None, out_dtype=torch.float32, flags=0, out=None):
     """INCWeightOnlyLinear.forward (modules.py:594-610) as one fused kernel."""
     require_cuda(x, "x")
+    _check_packed(qweight, qzeros, scales, bits, in_features, out_features, g_idx, input_scale, bias)
     lead = x.shape[:-1]
     x2 = x.reshape(-1, in_features)
     if not x2.is_contiguous():
@@ -146,6 +180,7 @@ def woq_linear(x, qweight, qzeros, scales, bias, bits, group_size, in_features, 
 def build_stream_layout(qweight, qzeros, scales, bits, group_size, in_features, out_features):
     """Derived B200-native layout for the small-batch 4-bit path (woq_stream.cu); None when not eligible."""
     require_cuda(qweight, "qweight")
+    _check_packed(qweight, qzeros, scales, bits, in_features, out_features)
     lib = _lib.load()
     nbytes = lib.b200woq_stream_layout_bytes(out_features, in_features, bits, group_size)
     if nbytes <= 0:
@@ -160,6 +195,10 @@ def woq_linear_stream(x, stream_layout, bias, bits, group_size, in_features, out
                       out_dtype=torch.float32, flags=0, out=None):
     """INCWeightOnlyLinear.forward for M <= 4 on the stream layout (per-warp TMA bulk-copy rings)."""
     require_cuda(x, "x")
+    if stream_layout.dtype != torch.uint8 or not stream_layout.is_cuda:
+        raise _lib.B200WOQError("stream_layout must be the uint8 CUDA tensor returned by build_stream_layout")
+    if input_scale is not None and (input_scale.dtype != torch.float32 or not input_scale.is_contiguous()):
+        raise _lib.B200WOQError("input_scale must be a contiguous float32 tensor")
     lead = x.shape[:-1]
     x2 = x.reshape(-1, in_features)
     if not x2.is_contiguous():

@@ -19,10 +19,17 @@ import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("B200WOQ_REFERENCE_ROOT", "/root/reference")
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")  # made by oracle/build_ref.py
 
 
 def reference_available() -> bool:
+    """The live tree (build container only)."""
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "neural_compressor"))
+
+
+def vendored_available() -> bool:
+    """The verbatim copy under oracle/_ref (travels to the GPU box; used by bench.py's reference / cpu_baseline legs)."""
+    return os.path.isdir(os.path.join(VENDORED_ROOT, "neural_compressor", "torch"))
 
 
 def _install_stubs():
@@ -65,12 +72,16 @@ def _install_stubs():
 
 def load_reference():
     """Return the imported `neural_compressor` package of the reference (CPU forced)."""
-    if not reference_available():
-        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    if reference_available():
+        root = REFERENCE_ROOT
+    elif vendored_available():
+        root = VENDORED_ROOT
+    else:
+        raise RuntimeError(f"reference not found at {REFERENCE_ROOT} nor vendored under {VENDORED_ROOT}")
     os.environ.setdefault("INC_TARGET_DEVICE", "cpu")  # torch/utils/auto_accelerator.py:436-442
     _install_stubs()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import neural_compressor  # noqa: F401
     import neural_compressor.torch.quantization  # noqa: F401
 

@@ -24,6 +24,42 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+# ---- measured parity numbers: every GPU parity test that is not bit-exact records what it measured; the session writes
+# them to gpurun_out/parity_r02.json (merged back by gpurun) and the committed copy lives in profiles/r02_parity.json
+_PARITY = {}
+
+
+def record_parity(key, value):
+    _PARITY[key] = value
+
+
+@pytest.fixture(scope="session")
+def parity_log():
+    return record_parity
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY:
+        return
+    import json
+
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, "parity_r02.json")
+        data = {}
+        if os.path.exists(path):
+            try:
+                data = json.load(open(path))
+            except Exception:
+                data = {}
+        data.update(_PARITY)
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
 

@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_json_line():
-    env = dict(os.environ, OMP_NUM_THREADS="4")
+    # B200WOQ_BENCH_TINY: toy layer shapes, so the contract (not a measurement) is checked in seconds
+    env = dict(os.environ, OMP_NUM_THREADS="4", B200WOQ_BENCH_TINY="1")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
@@ -20,7 +21,9 @@ def test_reference_arm_json_line():
               "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline", "impl"):
         assert k in d, k
     assert d["impl"] == "reference" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    vendored = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "neural_compressor")) or os.path.isdir("/root/reference")
+    assert d["cpu_baseline"]["kind"] == ("reference" if vendored else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["cpu_baseline"]["value"] == d["value"] > 0
     assert d["e2e"] == dict(value=d["value"], unit=d["unit"], h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     assert "workload" in d["config"] and "model" not in d["config"]

@@ -347,3 +347,34 @@ def test_minmax_cols(ops):
     ops.minmax_cols_accumulate(x[:100].to(DEV), mx, mn)
     ops.minmax_cols_accumulate(x[100:].to(DEV), mx, mn)
     assert torch.equal(mx.cpu(), x.max(0)[0]) and torch.equal(mn.cpu(), x.min(0)[0])
+
+
+# ------------------------------------------------------------------ robustness of the packed module
+def test_module_survives_dtype_casts_and_large_bf16_activations(ops):
+    """`model.to(torch.bfloat16)` must not re-type the fp16 scales the kernels reinterpret, and bf16 / fp32 activations
+    above the fp16 range (65504) must not overflow inside the small-batch kernels."""
+    from neural_compressor_b200.algorithms.modules import B200WeightOnlyLinear
+
+    g = torch.Generator().manual_seed(5)
+    N, K = 256, 512
+    W = torch.randn(N, K, generator=g) * 0.02
+    r = ops.rtn_quant_pack(W.to(DEV), 4, 128, True)
+    mod = B200WeightOnlyLinear(K, N, bits=4, group_size=128, device=DEV)
+    mod.set_packed(r["qweight"], r["qzeros"], r["scales"], None)
+    x16 = torch.randn(2, K, generator=g).half().to(DEV)
+    y0 = mod(x16).float()
+    scales0 = mod.scales.clone()
+    mod = mod.to(torch.bfloat16).float().half()
+    assert mod.scales.dtype == torch.float16 and torch.equal(mod.scales, scales0) and mod.bias.dtype == torch.float16
+    assert torch.equal(mod(x16).float(), y0)
+    wref = O.recover_fp16(r["qweight"].cpu(), r["qzeros"].cpu(), r["scales"].cpu(), 4, 128, K, N).float()
+    for dtype in (torch.bfloat16, torch.float32):
+        for rows in (1, 3, 16):
+            x = (torch.randn(rows, K, generator=g) * 3e5).to(dtype)      # far above 65504
+            y = mod(x.to(DEV))
+            assert y.dtype == dtype and torch.isfinite(y).all()
+            ref = x.float() @ wref.t()
+            assert _rel(y.float().cpu(), ref) < 1e-2, (dtype, rows)
+    # a re-typed scales tensor handed to the raw op is rejected, not reinterpreted
+    with pytest.raises(Exception):
+        ops.woq_linear(x16, r["qweight"], r["qzeros"], r["scales"].to(torch.bfloat16), None, 4, 128, K, N)
