@@ -151,6 +151,24 @@ int b200woq_hessian_accumulate(const void* X, int x_dtype, int64_t T, int64_t C,
 int b200woq_hessian_finalize(float* H, int64_t C, double nsamples, float percdamp, uint8_t* dead_mask,
                              float* scratch, void* stream);
 
+/* K2 -- the inverse Cholesky factor of the fasterquant prologue (gptq.py:1228-1231:
+ *   H = cholesky(H); H = cholesky_inverse(H); H = cholesky(H, upper=True)): U fp32 [C,C] upper triangular with
+ * U^T U = H^-1 (zeros below the diagonal), from ONE blocked Cholesky of the index-reversed matrix plus ONE blocked
+ * triangular inverse (U = J inv(chol(J H J)) J), exact fp32 FFMA tiles (cholinv.cu).  H [C,C] is the full symmetric
+ * damped Hessian (output of b200woq_hessian_finalize) and is left untouched.  `workspace` (16-byte aligned,
+ * b200woq_cholinv_workspace_bytes(C) bytes) holds two padded C x C buffers.  `info` (device int) receives 0 on
+ * success or 1 + the first (index-reversed) column whose pivot is not positive -- where the reference's
+ * torch.linalg.cholesky raises; U then holds NaNs.  Stream-ordered, no host synchronisation. */
+int64_t b200woq_cholinv_workspace_bytes(int64_t C);
+int b200woq_cholinv_upper(const float* H, int64_t C, float* U, void* workspace, int64_t workspace_bytes, int* info,
+                          void* stream);
+
+/* b200woq_hessian_finalize followed by b200woq_cholinv_upper on the finalized matrix (SURVEY §8b
+ * `hessian_finalize_cholinv_upper`): Hsum is finalized in place, U receives the factor. */
+int b200woq_hessian_finalize_cholinv_upper(float* Hsum, int64_t C, double nsamples, float percdamp,
+                                           uint8_t* dead_mask, float* scratch, float* U, void* workspace,
+                                           int64_t workspace_bytes, int* info, void* stream);
+
 /* Workspace of b200woq_gptq_fasterquant: the transposed error block Err^T fp32 [blocksize, N].  When the process
  * runs with B200WOQ_LAZY_TC=1 (opt-in tensor-core lazy update, gptq_tc.cu) it also holds the TF32 hi/lo splits of
  * Err^T and of Hinv: + 2*blocksize*N + 2*C*C floats. */
@@ -171,6 +189,11 @@ int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8_t* dead_ma
                              int blocksize, int groupsize, int bits, int sym, int flags, uint8_t* codes, float* Q,
                              float* scale, float* zero, float* losses, void* workspace,
                              int64_t workspace_bytes, void* stream);
+
+/* Fake-quant weights from codes: Q[n,c] = scale[n,g(c)] * (codes[n,c] - zero[n,g(c)]), bit-identical to the Q the
+ * column loop emits (Quantizer.quantize, gptq.py:1636-1637).  Lets row-sharded ranks exchange u8 codes + params only. */
+int b200woq_gptq_rebuild_q(const uint8_t* codes, const float* scale, const float* zero, int64_t N, int64_t C,
+                           int groupsize, float* Q, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K5  AWQ statistics (awq.py:131-154) and search losses (awq.py:343-344, 452-453)

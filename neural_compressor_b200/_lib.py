@@ -42,10 +42,15 @@ _SIGS = {
                                               c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200woq_hessian_accumulate": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "b200woq_hessian_finalize": (c_int, [c_void_p, c_int64, c_double, c_float, c_void_p, c_void_p, c_void_p]),
+    "b200woq_cholinv_workspace_bytes": (c_int64, [c_int64]),
+    "b200woq_cholinv_upper": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200woq_hessian_finalize_cholinv_upper": (c_int, [c_void_p, c_int64, c_double, c_float, c_void_p, c_void_p, c_void_p,
+                                                       c_void_p, c_int64, c_void_p, c_void_p]),
     "b200woq_gptq_workspace_bytes": (c_int64, [c_int64, c_int64, c_int]),
     "b200woq_gptq_fasterquant": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int,
                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                          c_void_p]),
+    "b200woq_gptq_rebuild_q": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "b200woq_awq_weight_scale": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "b200woq_abs_colsum_accumulate": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "b200woq_mse_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),

@@ -115,11 +115,31 @@ class _HessianBank:
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
         self.nsamples = int(round(n.item()))
 
+    def reduce_to_owners(self, owner_of_slot: Dict[int, int]):
+        """Each raw accumulator is summed onto ONE owner rank (`dist.reduce`), which alone factorises it and then
+        broadcasts the inverse factor: the Cholesky chain is no longer replicated on every rank and there is no host
+        synchronisation here (the global sample count is cached by the engine after the first block)."""
+        import torch.distributed as dist
+
+        for slot, h in enumerate(self.acc):
+            dist.reduce(h, dst=owner_of_slot[slot], op=dist.ReduceOp.SUM)
+
+
+def slot_owners(n_slots: int, world: int) -> Dict[int, int]:
+    """Owner rank of each distinct Hessian of a block, in order of first use (Llama: q/k/v, o, gate/up, down)."""
+    return {i: i % world for i in range(n_slots)}
+
 
 def _dist_world():
     import torch.distributed as dist
 
     return dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+
+
+def _dist_rank():
+    import torch.distributed as dist
+
+    return dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
 
 
 class RAWGPTQuantizer:
@@ -288,8 +308,11 @@ class RAWGPTQuantizer:
 
     def _fasterquant_rows_sharded(self, W, Hinv, dead, cfg):
         """The rows of a layer are independent given Hinv (per-row scale/zero gptq.py:1544-1565, per-row updates
-        :1297-1304), so with several ranks each one runs the column loop on N/world rows and the codes,
-        scales, zeros and fake-quant weights are all-gathered (NCCL).  Bit-identical to the un-sharded result."""
+        :1297-1304), so with several ranks each one runs the column loop on N/world rows.  Only the u8
+        codes, the per-group scale / zero and the per-row losses are all-gathered (N*C + 8*N*G + 4*N bytes instead of
+        the 5*N*C bytes that shipping the fp32 fake-quant weights would cost); every rank rebuilds
+        Q = scale * (code - zero) itself, which is the very expression the column loop stores (gptq.py:1636-1637).
+        Bit-identical to the un-sharded result."""
         import torch.distributed as dist
 
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
@@ -300,13 +323,77 @@ class RAWGPTQuantizer:
         rank = dist.get_rank()
         rows = N // world
         part = ops.gptq_fasterquant(W[rank * rows:(rank + 1) * rows].contiguous(), Hinv, dead, cfg["block_size"],
-                                    cfg["group_size"], cfg["bits"], cfg["sym"], cfg["mse"])
+                                    cfg["group_size"], cfg["bits"], cfg["sym"], cfg["mse"], want_q=False)
         out = {}
-        for k, v in part.items():
+        for k in ("codes", "scale", "zero", "losses"):
+            v = part[k]
             full = torch.empty((N,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device)
             dist.all_gather_into_tensor(full, v.contiguous())
             out[k] = full
+        out["Q"] = ops.gptq_rebuild_q(out["codes"], out["scale"], out["zero"], cfg["group_size"])
         return out
+
+    def _global_nsamples(self, local_n: int) -> int:
+        """Sum of the ranks' sample counts.  Every block sees the same calibration set, so the (synchronising) all-reduce
+        runs once, in the first block, and the result is cached."""
+        if _dist_world() == 1:
+            return local_n
+        cached = getattr(self, "_nsamples_cache", None)
+        if cached is None or cached[0] != local_n:
+            import torch.distributed as dist
+
+            n = torch.tensor([float(local_n)], device=self.device)
+            dist.all_reduce(n, op=dist.ReduceOp.SUM)
+            cached = self._nsamples_cache = (local_n, int(round(n.item())))
+        return cached[1]
+
+    def _share_factor(self, ent, owner: int, C: int, act_order: bool):
+        """Owner rank -> everyone: the inverse factor U (fp32 C x C), the dead-column mask, the factorisation status and,
+        with act_order, the permutation.  Runs on the current (side) stream; the owner first waits for its K2 chain."""
+        import torch.distributed as dist
+
+        cur = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
+        if _dist_rank() == owner:
+            if cur is not None and ent["done"] is not None:
+                cur.wait_event(ent["done"])
+        else:
+            ent["Hinv"] = torch.empty((C, C), dtype=torch.float32, device=self.device)
+            ent["dead"] = torch.empty(C, dtype=torch.uint8, device=self.device)
+            ent["info"] = torch.empty(1, dtype=torch.int32, device=self.device)
+            ent["perm"] = torch.empty(C, dtype=torch.int64, device=self.device) if act_order else None
+        dist.broadcast(ent["Hinv"], src=owner)
+        dist.broadcast(ent["dead"], src=owner)
+        dist.broadcast(ent["info"], src=owner)
+        if act_order:
+            dist.broadcast(ent["perm"], src=owner)
+        if cur is not None:
+            ent["done"] = torch.cuda.Event()
+            ent["done"].record()
+        ent["shared"] = True
+
+    def _queue_factor_status(self, infos, block_idx):
+        st = torch.stack(infos).max().reshape(1)
+        if st.is_cuda:
+            host = torch.empty(1, dtype=st.dtype, pin_memory=True)
+            host.copy_(st, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        else:
+            host, ev = st.clone(), None
+        self._pending_status = (ev, host, block_idx)
+
+    def _check_factor_status(self):
+        pend = getattr(self, "_pending_status", None)
+        if pend is None:
+            return
+        self._pending_status = None
+        ev, host, block_idx = pend
+        if ev is not None:
+            ev.synchronize()
+        if int(host.item()) != 0:
+            raise torch.linalg.LinAlgError(
+                f"block {block_idx}: a layer-input Hessian is not positive-definite after damping (cholinv status "
+                f"{int(host.item())}); raise percdamp")
 
     def _sync_time(self, key, t0):
         if self.profile:
@@ -327,6 +414,7 @@ class RAWGPTQuantizer:
             self.quantize_block(block_idx)
             if cb is not None:
                 cb(block_idx)
+        self._check_factor_status()
         return self.model
 
     @torch.no_grad()
@@ -361,14 +449,29 @@ class RAWGPTQuantizer:
             for h in handles:
                 h.remove()
             bank.begin_forward()  # drop the kept-alive inputs
-            bank.all_reduce()
+            world, rank = _dist_world(), _dist_rank()
+            # distinct Hessians in order of first use, each owned by one rank (all of them by rank 0 when world == 1)
+            slot_order: List[int] = []
+            for lname in layers:
+                sl = bank.layer_to_slot[lname]
+                if sl not in slot_order:
+                    slot_order.append(sl)
+            owners_by_pos = slot_owners(len(slot_order), world)
+            owner_of_slot = {sl: owners_by_pos[i] for i, sl in enumerate(slot_order)}
+            for sl in range(len(bank.acc)):
+                owner_of_slot.setdefault(sl, 0)
+            nsamples = self._global_nsamples(bank.nsamples)
+            if world > 1:
+                bank.reduce_to_owners(owner_of_slot)
             t0 = self._sync_time("hessian_fwd", t0)
-            # ---- Hessian -> inverse factor, once per distinct input (gptq.py:1189-1231) ----
+            # ---- Hessian -> inverse factor, once per distinct input, on its owner rank (gptq.py:1189-1231) ----
             # The distinct Hessians of a block (4 for Llama) and then its layers (7) are independent given the
-            # Hessians: the Cholesky chains (latency-bound panel factorisations) and the column loops (N/4 warps each,
-            # far from filling 148 SMs) are issued round-robin on side streams and joined before forward #2.
+            # Hessians: the K2 chains (latency-bound diagonal-tile factorisations) and the column loops (N/4 warps each,
+            # far from filling 148 SMs) are issued round-robin on side streams and joined before forward #2.  With
+            # several ranks the factor is broadcast right before the first layer that needs it, so the big (down_proj)
+            # factorisation on its owner overlaps the other layers' column loops on every rank.
             results = {}
-            by_slot: Dict[tuple, tuple] = {}
+            by_slot: Dict[tuple, dict] = {}
             keys_of_slot: Dict[int, set] = {}
             main = torch.cuda.current_stream(self.device) if self.device.type == "cuda" else None
             n_side = 1 if (self.profile or main is None) else max(1, int(os.environ.get("B200WOQ_GPTQ_STREAMS", "4")))
@@ -391,36 +494,40 @@ class RAWGPTQuantizer:
                 key = (slot, float(cfg["percdamp"]), bool(cfg["act_order"]))
                 if key in by_slot:
                     continue
-                with on(len(by_slot)):
-                    # finalize is in place: clone only when several configs share one raw accumulator
-                    Hc = bank.acc[slot].clone() if len(keys_of_slot[slot]) > 1 else bank.acc[slot]
-                    Hc, dead = ops.hessian_finalize(Hc, bank.nsamples, cfg["percdamp"])
-                    perm = None
-                    if cfg["act_order"]:
-                        perm = torch.argsort(torch.diag(Hc), descending=True)
-                        Hc = Hc[perm][:, perm].contiguous()
-                        dead = dead[perm].contiguous()
-                    t1 = time.perf_counter()
-                    Hinv = ops.cholesky_inverse_upper(Hc)
-                    self._sync_time("cholesky", t1)
-                    done = torch.cuda.Event() if side else None
-                    if done is not None:
-                        done.record()
-                by_slot[key] = (Hinv, dead, perm, done)
-            # the row-sharded path issues NCCL collectives: keep those on one stream so every rank orders them alike
-            fq_side = side if _dist_world() == 1 else []
-            if side and not fq_side:
-                for st in side:
-                    main.wait_stream(st)
+                ent = dict(Hinv=None, dead=None, perm=None, info=None, done=None, shared=world == 1,
+                           owner=owner_of_slot[slot], C=bank.acc[slot].shape[0], act_order=bool(cfg["act_order"]))
+                if ent["owner"] == rank:
+                    with on(len(by_slot)):
+                        # finalize is in place: clone only when several configs share one raw accumulator
+                        Hc = bank.acc[slot].clone() if len(keys_of_slot[slot]) > 1 else bank.acc[slot]
+                        Hc, dead = ops.hessian_finalize(Hc, nsamples, cfg["percdamp"])
+                        perm = None
+                        if cfg["act_order"]:
+                            perm = torch.argsort(torch.diag(Hc), descending=True)
+                            Hc = Hc[perm][:, perm].contiguous()
+                            dead = dead[perm].contiguous()
+                        t1 = time.perf_counter()
+                        info = torch.zeros(1, dtype=torch.int32, device=self.device)
+                        Hinv = ops.cholesky_inverse_upper(Hc, info=info, check=False)
+                        self._sync_time("cholesky", t1)
+                        done = torch.cuda.Event() if side else None
+                        if done is not None:
+                            done.record()
+                    ent.update(Hinv=Hinv, dead=dead, perm=perm, info=info, done=done)
+                by_slot[key] = ent
+            fq_side = side
             for li, (lname, layer) in enumerate(layers.items()):
                 cfg = self.get_layer_config(self.full_name(lname, block_idx))
                 key = (bank.layer_to_slot[lname], float(cfg["percdamp"]), bool(cfg["act_order"]))
-                Hinv, dead, perm, done = by_slot[key]
+                ent = by_slot[key]
                 # ---- fasterquant (gptq.py:704-713) ----
                 t1 = time.perf_counter()
                 with (torch.cuda.stream(fq_side[li % len(fq_side)]) if fq_side else contextlib.nullcontext()):
-                    if fq_side and done is not None:
-                        torch.cuda.current_stream(self.device).wait_event(done)
+                    if not ent["shared"]:
+                        self._share_factor(ent, ent["owner"], ent["C"], ent["act_order"])
+                    elif fq_side and ent["done"] is not None:
+                        torch.cuda.current_stream(self.device).wait_event(ent["done"])
+                    Hinv, dead, perm = ent["Hinv"], ent["dead"], ent["perm"]
                     W = layer.weight.data
                     W = (W.t() if _is_conv1d(layer) else W).float()
                     W = (W[:, perm] if perm is not None else W).contiguous().clone()
@@ -436,6 +543,7 @@ class RAWGPTQuantizer:
                 logger.info(f"block {block_idx} {lname}: error {r['losses'].sum().item():.6f}" if self.profile else
                             f"block {block_idx} {lname} quantized")
                 self._sync_time("fasterquant", t1)
+            infos = [e["info"] for e in by_slot.values() if e["info"] is not None]
             for st in fq_side:
                 main.wait_stream(st)
             del bank, by_slot
@@ -450,6 +558,12 @@ class RAWGPTQuantizer:
                 else:
                     self.cache_args[0][j] = out
             self.cache_kwargs["batch_num"] = batch_num
+            # factorisation status of this group's Hessians: the reference's torch.linalg.cholesky raises on a
+            # non-positive-definite H (gptq.py:1228).  The status is copied to pinned host memory asynchronously and
+            # examined when the NEXT block starts (or at the end of the run), so no block ever waits on the host.
+            self._check_factor_status()
+            if infos:
+                self._queue_factor_status(infos, block_idx)
             t0 = self._sync_time("propagate", t0)
             # ---- export: pack on the device (gptq.py:769-849) ----
             for lname, layer in layers.items():

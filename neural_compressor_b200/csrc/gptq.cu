@@ -407,6 +407,31 @@ int lazy_tc_update(const LazyTcPlan* plan, float* W, int64_t N, int64_t C, int64
 
 using namespace b200woq;
 
+// Q[n,c] = scale[n,g] * (code[n,c] - zero[n,g])  -- exactly the value the column loop stores (Quantizer.quantize,
+// gptq.py:1636-1637), recomputed from the codes so that multi-GPU row shards only have to exchange u8 codes + params.
+__global__ void gptq_rebuild_q_kernel(const uint8_t* __restrict__ codes, const float* __restrict__ scale,
+                                      const float* __restrict__ zero, int64_t N, int64_t C, int g, int G,
+                                      float* __restrict__ Q) {
+  const int64_t total = N * C;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = idx / C, c = idx - n * C;
+    const int64_t gi = n * G + (g > 0 ? c / g : 0);
+    Q[idx] = __fmul_rn(scale[gi], __fsub_rn((float)codes[idx], zero[gi]));
+  }
+}
+
+extern "C" int b200woq_gptq_rebuild_q(const uint8_t* codes, const float* scale, const float* zero, int64_t N, int64_t C,
+                                      int groupsize, float* Q, void* stream) {
+  WOQ_CHECK_ARG(codes && scale && zero && Q && N > 0 && C > 0, "gptq_rebuild_q: bad arguments");
+  const int g = (groupsize <= 0 || groupsize > C) ? 0 : groupsize;
+  const int G = g ? (int)ceil_div(C, g) : 1;
+  int64_t b = ceil_div(N * C, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  gptq_rebuild_q_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, (cudaStream_t)stream>>>(codes, scale, zero, N, C, g, G, Q);
+  WOQ_LAUNCH_CHECK();
+  return 0;
+}
+
 static bool lazy_tc_enabled() {
   static const int v = getenv("B200WOQ_LAZY_TC") ? atoi(getenv("B200WOQ_LAZY_TC")) : 0;
   return v != 0;

@@ -246,26 +246,64 @@ def hessian_finalize(Hsum: torch.Tensor, nsamples: float, percdamp: float):
     return Hsum, dead
 
 
-def cholesky_inverse_upper(H: torch.Tensor) -> torch.Tensor:
-    """Upper Cholesky factor U of H^-1 (U^T U = H^-1), gptq.py:1228-1231.
+_CHOL_WS = {}
 
-    The reference chains chol -> cholesky_inverse -> chol(upper) (4/3 C^3 flop).  U is unique, so it can be had
-    with half the work from the "reversed" factorisation: with J the exchange matrix, J H J = L L^T gives
-    H = (J L J)(J L J)^T with J L J upper triangular, hence H^-1 = (J L J)^-T (J L J)^-1 and U = (J L J)^-1 --
-    one potrf + one triangular solve (2/3 C^3 + trsm).  Same matrix, fewer roundings.  B200WOQ_CHOLINV=chain
-    selects the reference's three-step chain.  Round 1: cuSOLVER/cuBLAS through torch.linalg (library calls)."""
+
+def _cholinv_workspace(device, nbytes: int) -> torch.Tensor:
+    """One workspace per (device, stream): concurrent factorisations on side streams must not share buffers."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _CHOL_WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _CHOL_WS[key] = ws
+    return ws
+
+
+def release_workspaces():
+    """Drop the cached K2 / dequant-GEMM workspaces (about 1 GB per stream after a C = 11008 factorisation)."""
+    _CHOL_WS.clear()
+    _WS_CACHE.clear()
+
+
+def cholesky_inverse_upper(H: torch.Tensor, info: Optional[torch.Tensor] = None, check: bool = True) -> torch.Tensor:
+    """Upper Cholesky factor U of H^-1 (U^T U = H^-1), gptq.py:1228-1231 -- K2, hand-written (cholinv.cu).
+
+    The reference chains chol -> cholesky_inverse -> chol(upper) (4/3 C^3 flop).  U is unique, so it is computed with
+    half the work from the index-reversed factorisation: with J the exchange matrix, J H J = L L^T gives
+    H = (J L J)(J L J)^T with J L J upper triangular, hence U = (J L J)^-1 = J L^-1 J: one blocked Cholesky and one
+    blocked triangular inverse, exact fp32 FFMA.  `info` (int32[1] device tensor) receives the factorisation status
+    (0 = ok); with check=True (default) the status is read back (one host sync) and a failed factorisation raises like
+    the reference's torch.linalg.cholesky; the engine passes check=False and tests all statuses once per block.
+    B200WOQ_CHOLINV=torch selects the cuSOLVER/cuBLAS cross-check path (library calls, not the product path)."""
     import os
 
-    if os.environ.get("B200WOQ_CHOLINV", "ul") == "chain":
+    require_cuda(H, "H")
+    assert H.dtype == torch.float32 and H.dim() == 2 and H.shape[0] == H.shape[1]
+    mode = os.environ.get("B200WOQ_CHOLINV", "b200")
+    if mode == "chain":
         L = torch.linalg.cholesky(H)
         Hi = torch.cholesky_inverse(L)
         return torch.linalg.cholesky(Hi, upper=True).contiguous()
-    # cholesky_ex(check_errors=False): no device->host sync on the factorisation status (a failed factorisation
-    # yields NaNs that surface in the codes; the damped Hessian is positive definite by construction)
-    Lf = torch.linalg.cholesky_ex(H.flip(0, 1), check_errors=False).L
-    Ut = Lf.flip(0, 1)  # upper triangular, H = Ut Ut^T
-    eye = torch.eye(H.shape[0], dtype=H.dtype, device=H.device)
-    return torch.linalg.solve_triangular(Ut, eye, upper=True).contiguous()
+    if mode == "torch":
+        Lf = torch.linalg.cholesky(H.flip(0, 1))
+        Ut = Lf.flip(0, 1)  # upper triangular, H = Ut Ut^T
+        eye = torch.eye(H.shape[0], dtype=H.dtype, device=H.device)
+        return torch.linalg.solve_triangular(Ut, eye, upper=True).contiguous()
+    C = H.shape[0]
+    lib = _lib.load()
+    nbytes = lib.b200woq_cholinv_workspace_bytes(C)
+    ws = _cholinv_workspace(H.device, nbytes)
+    U = torch.empty_like(H)
+    if info is None:
+        info = torch.zeros(1, dtype=torch.int32, device=H.device)
+    check_rc = lib.b200woq_cholinv_upper(ptr(H), C, ptr(U), ptr(ws), ws.numel(), ptr(info), stream_ptr(H.device))
+    _lib.check(check_rc, "cholinv_upper")
+    if check:
+        st = int(info.item())
+        if st != 0:
+            raise torch.linalg.LinAlgError(
+                f"cholinv_upper: the Hessian is not positive-definite (pivot {C - st} of {C}); raise percdamp")
+    return U
 
 
 def gptq_fasterquant(W: torch.Tensor, Hinv: torch.Tensor, dead_mask: Optional[torch.Tensor], blocksize=128,
@@ -290,6 +328,18 @@ def gptq_fasterquant(W: torch.Tensor, Hinv: torch.Tensor, dead_mask: Optional[to
                                        1 if mse else 0, ptr(codes), ptr(Q), ptr(scale), ptr(zero), ptr(losses),
                                        ptr(ws), nbytes, stream_ptr(dev)), "gptq_fasterquant")
     return dict(codes=codes, Q=Q, scale=scale, zero=zero, losses=losses)
+
+
+def gptq_rebuild_q(codes: torch.Tensor, scale: torch.Tensor, zero: torch.Tensor, groupsize: int) -> torch.Tensor:
+    """Q = scale * (codes - zero), the fake-quant weights of gptq.py:1636-1637, from the u8 codes (bit-identical to the Q
+    `gptq_fasterquant` emits)."""
+    require_cuda(codes, "codes")
+    assert codes.dtype == torch.uint8 and scale.dtype == torch.float32 and zero.dtype == torch.float32
+    N, C = codes.shape
+    Q = torch.empty((N, C), dtype=torch.float32, device=codes.device)
+    check(_lib.load().b200woq_gptq_rebuild_q(ptr(codes), ptr(scale.contiguous()), ptr(zero.contiguous()), N, C, groupsize,
+                                             ptr(Q), stream_ptr(codes.device)), "gptq_rebuild_q")
+    return Q
 
 
 # ------------------------------------------------------------------ K5/K7 statistics

@@ -68,17 +68,73 @@ def _rows_worker(rank, world, port, ret):
     full = lay.fasterquant(W, 128, 0.01, 32)
     hinv = full["hinv"]
 
-    def fake_fasterquant(Wp, Hinv, dead, blocksize, groupsize, bits, sym, mse):
+    def fake_fasterquant(Wp, Hinv, dead, blocksize, groupsize, bits, sym, mse, want_q=True):
         # stand-in for the CUDA column loop: the oracle on this rank's rows (the product path never does this)
         sub = O.GPTQLayerOracle(Wp.shape[0], C, bits=bits, sym=sym).fasterquant(Wp, blocksize, 0.01, groupsize, hinv=Hinv)
-        return dict(Q=sub["Q"], scale=sub["scale"], zero=sub["zero"])
+        codes = (O.GPTQLayerOracle.export_codes(sub["Q"], sub["scale"], sub["zero"], groupsize, sym) + 8).to(torch.uint8)
+        assert not want_q  # the sharded path must not ask for (nor ship) the fp32 fake-quant weights
+        return dict(codes=codes, Q=None, scale=sub["scale"], zero=sub["zero"], losses=sub["losses"].sum(1))
+
+    def fake_rebuild_q(codes, scale, zero, groupsize):
+        # stand-in for b200woq_gptq_rebuild_q: scale * (code - zero), one rounded subtract and one rounded multiply
+        g = codes.shape[1] // scale.shape[1]
+        return scale.repeat_interleave(g, 1) * (codes.float() - zero.repeat_interleave(g, 1))
 
     G.ops.gptq_fasterquant = fake_fasterquant
+    G.ops.gptq_rebuild_q = fake_rebuild_q
     eng = G.RAWGPTQuantizer.__new__(G.RAWGPTQuantizer)
     out = eng._fasterquant_rows_sharded(W, hinv, None, dict(block_size=128, group_size=32, bits=4, sym=True, mse=False))
+    # only codes + params travel; the locally rebuilt Q is bit-identical to the un-sharded oracle's fake-quant weights
     ok = all(torch.equal(out[k], full[k]) for k in ("Q", "scale", "zero"))
+    ok = ok and out["codes"].dtype == torch.uint8 and tuple(out["codes"].shape) == (N, C)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
+
+
+def _owner_worker(rank, world, port, ret):
+    """Owner schedule of the N>1 path: raw Hessians are reduced onto their owner ranks, each owner alone holds the sum
+    and (after its factorisation) broadcasts factor / dead mask / status / permutation to everyone."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import neural_compressor_b200.algorithms.gptq as G
+
+    C = 12
+    g = torch.Generator().manual_seed(3)
+    parts = [[torch.randn(C, C, generator=g) for _ in range(3)] for _ in range(world)]  # [rank][slot]
+    bank = G._HessianBank(torch.device("cpu"))
+    bank.acc = [p.clone() for p in parts[rank]]
+    owners = G.slot_owners(3, world)
+    ok = owners == {0: 0, 1: 1 % world, 2: 2 % world}
+    bank.reduce_to_owners(owners)
+    for slot in range(3):
+        if owners[slot] == rank:
+            ok = ok and torch.allclose(bank.acc[slot], sum(parts[r][slot] for r in range(world)), atol=1e-5)
+    eng = G.RAWGPTQuantizer.__new__(G.RAWGPTQuantizer)
+    eng.device = torch.device("cpu")
+    n = eng._global_nsamples(5 + rank)
+    ok = ok and n == sum(5 + r for r in range(world)) and eng._global_nsamples(5 + rank) == n  # second call: cached
+    for slot in range(3):
+        own = owners[slot]
+        ent = dict(Hinv=None, dead=None, perm=None, info=None, done=None, shared=False)
+        if own == rank:
+            ent.update(Hinv=bank.acc[slot].clone(), dead=torch.arange(C).to(torch.uint8), info=torch.tensor([slot], dtype=torch.int32),
+                       perm=torch.randperm(C, generator=g))
+        eng._share_factor(ent, own, C, True)
+        gathered = [torch.zeros(C, C) for _ in range(world)]
+        dist.all_gather(gathered, ent["Hinv"])
+        ok = ok and all(torch.equal(gathered[0], t) for t in gathered) and int(ent["info"]) == slot and ent["shared"]
+        ok = ok and ent["perm"].dtype == torch.int64 and sorted(ent["perm"].tolist()) == list(range(C))
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_owner_reduce_and_factor_broadcast_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29912 + os.getpid() % 200
+    mp.spawn(_owner_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
 
 
 def test_row_sharded_fasterquant_is_exact_gloo_world2():

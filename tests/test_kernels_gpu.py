@@ -378,3 +378,46 @@ def test_module_survives_dtype_casts_and_large_bf16_activations(ops):
     # a re-typed scales tensor handed to the raw op is rejected, not reinterpreted
     with pytest.raises(Exception):
         ops.woq_linear(x16, r["qweight"], r["qzeros"], r["scales"].to(torch.bfloat16), None, 4, 128, K, N)
+
+
+# ------------------------------------------------------------------ K2: hand-written inverse Cholesky factor
+@pytest.mark.parametrize("C", [40, 128, 256, 384, 1032, 2048])
+def test_cholinv_upper_vs_reference_chain(ops, C, parity_log):
+    """cholinv.cu against the reference's chain cholesky -> cholesky_inverse -> cholesky(upper) (gptq.py:1228-1231) run
+    by the oracle in fp32 (LAPACK) and against the same chain in fp64 (the truth both approximate)."""
+    g = torch.Generator().manual_seed(C)
+    X = torch.randn(3 * C, C, generator=g) * torch.exp(torch.randn(C, generator=g) * 0.7)
+    H = (X.t() @ X) * (2.0 / (3 * C))
+    H[torch.arange(C), torch.arange(C)] += 0.01 * torch.diag(H).mean()
+    U = ops.cholesky_inverse_upper(H.to(DEV).contiguous())
+    assert torch.equal(U, torch.triu(U))                       # exact zeros below the diagonal, like torch's upper=True
+    ref32 = O.GPTQLayerOracle.cholesky_inverse_upper(H)
+    Hd = H.double()
+    ref64 = torch.linalg.cholesky(torch.cholesky_inverse(torch.linalg.cholesky(Hd)), upper=True)
+    scale = ref64.abs().max().item()
+    e_ours = (U.cpu().double() - ref64).abs().max().item() / scale
+    e_ref = (ref32.double() - ref64).abs().max().item() / scale
+    parity_log(f"cholinv/C{C}", dict(ours_vs_fp64=e_ours, lapack_fp32_chain_vs_fp64=e_ref))
+    # the one-factorisation route must be at least as accurate as the reference's own fp32 chain (x4 slack), and fp32-grade
+    assert e_ours <= max(4 * e_ref, 2e-6), (e_ours, e_ref)
+    assert (U.cpu() - ref32).abs().max().item() / scale < 1e-4
+
+
+def test_cholinv_not_positive_definite_raises(ops):
+    H = torch.eye(256)
+    H[100, 100] = -1.0
+    with pytest.raises(torch.linalg.LinAlgError):
+        ops.cholesky_inverse_upper(H.to(DEV))
+
+
+def test_gptq_rebuild_q_matches_column_loop(ops, golden_gptq):
+    """Q rebuilt from the codes (what row-sharded ranks do) is bit-identical to the Q the column loop emits."""
+    W = golden_gptq["W"]
+    for run in golden_gptq["runs"][:5]:
+        v = run["cfg"]
+        if v["act_order"]:
+            continue
+        r = ops.gptq_fasterquant(W.clone().to(DEV), golden_gptq["Hinv"].contiguous().to(DEV), None, v["blocksize"],
+                                 v["group_size"], v["bits"], v["sym"], v["mse"])
+        Q2 = ops.gptq_rebuild_q(r["codes"], r["scale"], r["zero"], v["group_size"])
+        assert torch.equal(Q2, r["Q"]), v
