@@ -330,6 +330,244 @@ __global__ void __launch_bounds__(1024) woq_gemm_stream_kernel(const Params p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (default): one CTA per SM, each owning a contiguous range of WHOLE strips (no cross-CTA
+// reduction, deterministic); the CTA's records (strip-major = one contiguous byte range) are cut into W equal
+// contiguous pieces, one per warp, regardless of strip boundaries, so every warp streams the same number of bytes
+// whatever G is (the strip-per-CTA kernel leaves warps idle when G % warps != 0 and whole SMs idle when
+// strips % 148 != 0).  A warp that crosses a strip boundary parks its partial sums in a slot; one __syncthreads at
+// the end, then a fixed-order reduction.  The footprint is kept under HALF an SM (<= 512 threads, <= ~110 KB of shared
+// memory) so that under programmatic dependent launch the NEXT layer's CTAs are co-resident and fill their rings from
+// HBM while this layer is still computing: the ~2 us dependent-launch latency and the ring-fill latency are hidden
+// behind the previous layer instead of serialising with it.
+struct PParams {
+  const void* x;
+  int x_dtype;
+  int M, K, N;
+  const uint8_t* recs;
+  int NI, g, G;
+  const void* bias;
+  int bias_dtype;
+  const float* input_scale;
+  void* y;
+  int y_dtype;
+  int W;          // warps per CTA
+  int nst;        // ring depth per warp
+  int n_strips;
+  int xs_ld;      // halves per staged x row (K + 32: 64-byte skew between batch rows)
+  int pdl;
+};
+constexpr int kSlots = 4;  // strip segments a warp's record range may touch
+
+template <int MODE, int NI_T>
+__global__ void __launch_bounds__(512) woq_gemm_persist_kernel(const PParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t = lane & 3;
+  const int NI = NI_T ? NI_T : p.NI;
+  const int g = NI * 32;
+  const int rec_bytes = NI * 512 + 96;
+  const int W = p.W, nst = p.nst, G = p.G;
+  // strips of this CTA, records of this warp (CTA-linear, strip-major)
+  const int s0 = (int)(((int64_t)p.n_strips * blockIdx.x) / gridDim.x);
+  const int s1 = (int)(((int64_t)p.n_strips * (blockIdx.x + 1)) / gridDim.x);
+  const int R = (s1 - s0) * G;
+  const int wa = (int)(((int64_t)R * warp) / W), wb = (int)(((int64_t)R * (warp + 1)) / W);
+  const int nrec = wb - wa;
+  // shared memory: [W rings: nst*rec_bytes][W*nst barriers][xs: M x xs_ld f16][xsum: M x G f32][slots][seg_first][zpad]
+  uint8_t* ring = smem_raw + (size_t)warp * nst * rec_bytes;
+  const uint32_t ring_u32 = smem_u32(ring);
+  uint8_t* after_rings = smem_raw + (size_t)W * nst * rec_bytes;
+  const uint32_t bars = smem_u32(after_rings) + (uint32_t)warp * nst * 8u;
+  __half* xs = reinterpret_cast<__half*>(after_rings + (((size_t)W * nst * 8 + 127) & ~(size_t)127));
+  float* xsum = reinterpret_cast<float*>(xs + (size_t)p.M * p.xs_ld);
+  float* slots = xsum + (((size_t)p.M * G + 3) & ~(size_t)3);                  // [W][kSlots][M][32]
+  int* seg_first = reinterpret_cast<int*>(slots + (size_t)W * kSlots * p.M * 32);  // [W] first local strip, [W] count
+  __half* zpad = reinterpret_cast<__half*>(seg_first + 2 * W);
+
+  const uint8_t* src = p.recs + ((size_t)s0 * G + wa) * rec_bytes;
+  if (lane == 0) {
+    for (int s = 0; s < nst; ++s) mbar_init(bars + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int pre = min(nst, nrec);
+    for (int i = 0; i < pre; ++i) {  // weights are constants: stream them before the dependency is resolved
+      mbar_expect_tx(bars + 8u * i, (uint32_t)rec_bytes);
+      bulk_load(ring_u32 + i * rec_bytes, src + (size_t)i * rec_bytes, (uint32_t)rec_bytes, bars + 8u * i);
+    }
+  }
+  if (p.pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+  }
+  // ---- stage x once per CTA (all warps, 8-element chunks round-robin): fp16 in the permuted / pre-scaled order of
+  // the strip kernel, plus X_g = per-group sums of the fp16-rounded activations
+  {
+    const int cpg = g >> 3;                 // chunks per group
+    const int nchunk = p.K >> 3;
+    const __half2 sixteenth = __float2half2_rn(0.0625f);
+    for (int m = 0; m < p.M; ++m) {
+      const int64_t row = (int64_t)m * p.K;
+      for (int kb = warp * 32; kb < nchunk; kb += W * 32) {
+        const int kc = kb + lane;
+        float csum = 0.f;
+        if (kc < nchunk) {
+          float v[8];
+          load8(p.x, p.x_dtype, row + (int64_t)kc * 8, v);
+          if (p.input_scale) {
+            float sc8[8];
+            load8(p.input_scale, B200WOQ_F32, (int64_t)kc * 8, sc8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] *= sc8[i];
+          }
+          __half2 h0 = __floats2half2_rn(v[0], v[4]), h1 = __floats2half2_rn(v[1], v[5]);
+          __half2 h2 = __floats2half2_rn(v[2], v[6]), h3 = __floats2half2_rn(v[3], v[7]);
+          const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+          csum = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+          h1 = __hmul2(h1, sixteenth);
+          h3 = __hmul2(h3, sixteenth);
+          uint4 o;
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(xs + (size_t)m * p.xs_ld + (size_t)kc * 8) = o;
+        }
+        // group sums: cpg chunks per group (the host only takes this kernel when cpg is a power of two <= 32)
+        {
+          for (int o = cpg >> 1; o > 0; o >>= 1) csum += __shfl_xor_sync(0xffffffffu, csum, o);
+          if ((lane & (cpg - 1)) == 0 && kc < nchunk) xsum[(size_t)m * G + kc / cpg] = csum;
+        }
+      }
+    }
+    for (int e = threadIdx.x * 8; e < g + 32; e += blockDim.x * 8) *reinterpret_cast<uint4*>(zpad + e) = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+
+  float acc[2][4], accg[2][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[a][c] = accg[a][c] = 0.f;
+  const bool live = gq < p.M;
+  const __half* xrow = (live ? xs + (size_t)gq * p.xs_ld : zpad) + t * 8;
+  const int m0 = 2 * t;
+  const float* xsum0 = xsum + (size_t)min(m0, p.M - 1) * G;
+  const float* xsum1 = xsum + (size_t)min(m0 + 1, p.M - 1) * G;
+  const float keep0 = (m0 < p.M) ? 1.f : 0.f, keep1 = (MODE != 0 && m0 + 1 < p.M) ? 1.f : 0.f;
+
+  int sl = wa / G;            // current local strip
+  int gi = wa - sl * G;       // current group within the strip
+  const int first_sl = sl;
+  int nseg = 0;
+  auto flush = [&]() {
+    float* dst = slots + ((size_t)(warp * kSlots + nseg) * p.M) * 32;
+#pragma unroll
+    for (int half = 0; half < (MODE == 0 ? 1 : 2); ++half) {
+      const int m = 2 * t + half;
+      if (m < p.M)
+        *reinterpret_cast<float4*>(dst + (size_t)m * 32 + 4 * gq) =
+            make_float4(acc[0][half], acc[0][2 + half], acc[1][half], acc[1][2 + half]);
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][c] = 0.f;
+    ++nseg;
+  };
+
+  int s = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < nrec; ++i) {
+    mbar_wait(bars + 8u * s, phase);
+    const uint8_t* rec = ring + s * rec_bytes;
+    const uint2 sc = *reinterpret_cast<const uint2*>(rec + NI * 512 + gq * 8);
+    const uint32_t zq = *reinterpret_cast<const uint32_t*>(rec + NI * 512 + 64 + gq * 4);
+    const float x0 = xsum0[gi] * keep0;
+    const float x1 = (MODE != 0) ? xsum1[gi] * keep1 : 0.f;
+    const uint4* wsrc = reinterpret_cast<const uint4*>(rec) + lane;
+    const __half* xptr = live ? xrow + (size_t)gi * g : xrow;
+    auto step = [&](int it, auto first) {
+      const uint4 wv = wsrc[it * 32];
+      const uint4 v = *reinterpret_cast<const uint4*>(xptr + it * 32);
+      const uint32_t wr[4] = {wv.x, wv.y, wv.z, wv.w};
+      uint32_t P[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const uint32_t w8 = wr[r] >> 8;
+        P[r][0] = wr[r] & 0x000f000fu;
+        P[r][1] = wr[r] & 0x00f000f0u;
+        P[r][2] = w8 & 0x000f000fu;
+        P[r][3] = w8 & 0x00f000f0u;
+      }
+      if (decltype(first)::value) {
+        mma_16816_zero(accg[0], P[0][0], P[1][0], P[0][1], P[1][1], v.x, v.y);
+        mma_16816_zero(accg[1], P[2][0], P[3][0], P[2][1], P[3][1], v.x, v.y);
+      } else {
+        mma_16816(accg[0], P[0][0], P[1][0], P[0][1], P[1][1], v.x, v.y);
+        mma_16816(accg[1], P[2][0], P[3][0], P[2][1], P[3][1], v.x, v.y);
+      }
+      mma_16816(accg[0], P[0][2], P[1][2], P[0][3], P[1][3], v.z, v.w);
+      mma_16816(accg[1], P[2][2], P[3][2], P[2][3], P[3][3], v.z, v.w);
+    };
+    step(0, std::true_type{});
+    if (NI_T) {
+#pragma unroll
+      for (int it = 1; it < NI_T; ++it) step(it, std::false_type{});
+    } else {
+      for (int it = 1; it < NI; ++it) step(it, std::false_type{});
+    }
+    if (i + nst < nrec) {  // the stage is consumed (its words are in registers): refill it
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bars + 8u * s, (uint32_t)rec_bytes);
+        bulk_load(ring_u32 + s * rec_bytes, src + (size_t)(i + nst) * rec_bytes, (uint32_t)rec_bytes, bars + 8u * s);
+      }
+    }
+    if (++s == nst) {
+      s = 0;
+      phase ^= 1u;
+    }
+    const __half2 s01 = *reinterpret_cast<const __half2*>(&sc.x), s23 = *reinterpret_cast<const __half2*>(&sc.y);
+    const float sf[4] = {__low2float(s01), __high2float(s01), __low2float(s23), __high2float(s23)};
+    const float zf[4] = {(float)(zq & 0xffu), (float)((zq >> 8) & 0xffu), (float)((zq >> 16) & 0xffu), (float)(zq >> 24)};
+#pragma unroll
+    for (int tile = 0; tile < 2; ++tile) {
+      const float sa = sf[2 * tile], sb = sf[2 * tile + 1], za = zf[2 * tile], zb = zf[2 * tile + 1];
+      acc[tile][0] = fmaf(fmaf(accg[tile][0], 16777216.f, -za * x0), sa, acc[tile][0]);
+      acc[tile][2] = fmaf(fmaf(accg[tile][2], 16777216.f, -zb * x0), sb, acc[tile][2]);
+      if (MODE != 0) {
+        acc[tile][1] = fmaf(fmaf(accg[tile][1], 16777216.f, -za * x1), sa, acc[tile][1]);
+        acc[tile][3] = fmaf(fmaf(accg[tile][3], 16777216.f, -zb * x1), sb, acc[tile][3]);
+      }
+    }
+    if (++gi == G) {  // strip finished for this warp: park the partial sums
+      flush();
+      gi = 0;
+      ++sl;
+    }
+  }
+  if (gi != 0 && nrec > 0) flush();
+  if (lane == 0) {
+    seg_first[warp] = first_sl;
+    seg_first[W + warp] = nseg;
+  }
+  __syncthreads();
+  // fixed-order reduction over the warps' segments -> deterministic
+  const int nloc = s1 - s0;
+  for (int e = threadIdx.x; e < nloc * p.M * 32; e += blockDim.x) {
+    const int nl = e & 31, m = (e >> 5) % p.M, ls = (e >> 5) / p.M;
+    float v = 0.f;
+    for (int w = 0; w < W; ++w) {
+      const int k = ls - seg_first[w];
+      if (k >= 0 && k < seg_first[W + w]) v += slots[((size_t)(w * kSlots + k) * p.M + m) * 32 + nl];
+    }
+    const int n = (s0 + ls) * 32 + nl;
+    if (p.bias) v += load_as_float(p.bias, p.bias_dtype, n);
+    store_from_float(p.y, p.y_dtype, (int64_t)m * p.N + n, v);
+  }
+}
+
 // optimum-format tensors -> strip records [N/32][G]: [NI x 32 lanes x int4 | 32 fp16 scales | 32 u8 zero-points]
 __global__ void build_stream_kernel(const int32_t* __restrict__ qweight, const int32_t* __restrict__ qzeros,
                                     const __half* __restrict__ scales, int N, int K, int g, int G, int NI, int rec_bytes,
@@ -411,7 +649,7 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
   const int g = eff_group(K, group_size);
   WOQ_CHECK_ARG(x && stream_layout && y && M > 0, "linear_forward_stream: null pointer / empty batch");
   WOQ_CHECK_ARG(stream_shape_ok(N, K, bits, g), "linear_forward_stream: unsupported shape");
-  WOQ_CHECK_ARG(M <= 4, "linear_forward_stream: M must be <= 4 (use b200woq_linear_forward)");
+  WOQ_CHECK_ARG(M <= 8, "linear_forward_stream: M must be <= 8 (use b200woq_linear_forward)");
   Params p = {};
   p.x = x;
   p.x_dtype = x_dtype;
@@ -429,6 +667,68 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
   p.y = y;
   p.y_dtype = y_dtype;
   p.pdl = (flags & 2) ? 1 : 0;
+  // ---- persistent kernel (default): see woq_gemm_persist_kernel
+  static const int impl = getenv("B200WOQ_STREAM_IMPL") ? atoi(getenv("B200WOQ_STREAM_IMPL")) : 1;
+  if (impl == 1) {
+    PParams q = {};
+    q.x = x; q.x_dtype = x_dtype; q.M = (int)M; q.K = (int)K; q.N = (int)N;
+    q.recs = (const uint8_t*)stream_layout; q.NI = g / 32; q.g = g; q.G = (int)(K / g);
+    q.bias = bias; q.bias_dtype = bias_dtype; q.input_scale = input_scale; q.y = y; q.y_dtype = y_dtype;
+    q.pdl = p.pdl; q.n_strips = (int)(N / 32); q.xs_ld = (int)K + 32;
+    const int sms_ = num_sms();
+    const int ctas = std::min(sms_, q.n_strips);
+    const int max_strips = (int)ceil_div(q.n_strips, ctas);
+    static const int env_w = getenv("B200WOQ_PERSIST_WARPS") ? atoi(getenv("B200WOQ_PERSIST_WARPS")) : 16;
+    static const int env_n = getenv("B200WOQ_PERSIST_NST") ? atoi(getenv("B200WOQ_PERSIST_NST")) : 0;
+    int Wp = std::max(1, std::min(env_w, 16));
+    const int rec_b = q.NI * 512 + 96;
+    // every warp needs work, and its contiguous range may touch at most kSlots strips
+    while (Wp > 1 && (int64_t)max_strips * q.G < 2ll * Wp) Wp /= 2;
+    auto segs = [&](int w) { return (int)(ceil_div((int64_t)max_strips * q.G, w) / q.G) + 2; };
+    auto smem_for = [&](int w, int n) {
+      size_t b = (size_t)w * n * rec_b;
+      b += ((size_t)w * n * 8 + 127) & ~(size_t)127;
+      b += (size_t)q.M * q.xs_ld * 2;
+      b += (((size_t)q.M * q.G + 3) & ~(size_t)3) * 4;
+      b += (size_t)w * kSlots * q.M * 32 * 4 + (size_t)2 * w * 4 + (size_t)(g + 32) * 2;
+      return (b + 127) & ~(size_t)127;
+    };
+    const size_t half_sm = (size_t)(227 * 1024) / 2 - 1024, full_sm = 226 * 1024;
+    const int cpg_ = g >> 3;
+    const bool cpg_ok = cpg_ <= 32 && (cpg_ & (cpg_ - 1)) == 0;  // the staging pass reduces X_g with in-warp shuffles
+    if (cpg_ok && segs(Wp) <= kSlots && smem_for(Wp, 1) <= full_sm) {
+      int n = env_n > 0 ? env_n : 4;
+      n = std::min<int>(n, kMaxStages);
+      while (n > 2 && smem_for(Wp, n) > half_sm) --n;         // prefer the co-resident (half-SM) footprint
+      while (n > 1 && smem_for(Wp, n) > full_sm) --n;
+      q.W = Wp; q.nst = n;
+      const size_t smem = smem_for(Wp, n);
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3((unsigned)ctas);
+      cfg.blockDim = dim3((unsigned)(32 * Wp));
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = (cudaStream_t)stream_;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = q.pdl ? 1 : 0;
+#define PERSIST_LAUNCH(MODE_, NI_)                                                                                  \
+  do {                                                                                                              \
+    WOQ_CUDA(cudaFuncSetAttribute(woq_gemm_persist_kernel<MODE_, NI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)smem));                                                                      \
+    WOQ_CUDA(cudaLaunchKernelEx(&cfg, woq_gemm_persist_kernel<MODE_, NI_>, q));                                     \
+  } while (0)
+      if (M == 1) {
+        if (q.NI == 4) PERSIST_LAUNCH(0, 4); else PERSIST_LAUNCH(0, 0);
+      } else {
+        if (q.NI == 4) PERSIST_LAUNCH(1, 4); else PERSIST_LAUNCH(1, 0);
+      }
+#undef PERSIST_LAUNCH
+      count_launch(1);
+      return 0;
+    }
+  }
   // One CTA per 32-column strip; its wpc warps split K.  Every CTA of the grid must be resident at once (a second
   // wave would serialise behind the first): that caps warps per CTA at 64 / ceil(strips / SMs) and shared memory per
   // CTA at its share of the SM.  Within those caps: as many warps as keep >= 2 groups each (up to ~12 streaming warps

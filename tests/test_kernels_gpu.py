@@ -116,7 +116,7 @@ def test_woq_linear_fast_path_vs_oracle(ops, bits, sym, N, K, g):
 
 @pytest.mark.parametrize("sym", [True, False])
 @pytest.mark.parametrize("N,K,g", [(256, 512, 128), (96, 384, 32), (4096, 4096, 128), (1024, 2752, 64), (11008, 1024, 128),
-                                   (4096, 11008, 128), (160, 768, 256)])
+                                   (4096, 11008, 128), (160, 768, 256), (12288, 4096, 128)])
 def test_woq_linear_stream_layout_vs_oracle(ops, sym, N, K, g):
     """Small-batch TMA-streamed path on the derived stream layout (woq_stream.cu)."""
     gen = torch.Generator().manual_seed(N + K + g)
@@ -127,7 +127,7 @@ def test_woq_linear_stream_layout_vs_oracle(ops, sym, N, K, g):
     w_ref = O.recover_fp16(qw, qz, sc, 4, g, K, N).float()
     layout = ops.build_stream_layout(qw.to(DEV), qz.to(DEV), sc.to(DEV), 4, g, K, N)
     assert layout is not None
-    for M in (1, 2, 3, 4):
+    for M in (1, 2, 3, 4, 7, 8):
         x = torch.randn(M, K, generator=gen)
         ref = torch.nn.functional.linear(x, w_ref, bias.float())
         for xdt in (torch.float16, torch.float32, torch.bfloat16):
