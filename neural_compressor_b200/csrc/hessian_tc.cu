@@ -12,9 +12,12 @@
 //               (hessian_syrk_tc_kernel).  Only tiles touching the upper block triangle are computed; the rest is
 //               mirrored in b200woq_hessian_finalize.
 //   precision   the tensor core adds into its fp32 accumulator with truncation, so a long contraction drifts
-//               (measured 1.3e-5 relative after 8192 tokens).  The token loop is therefore cut into SEGMENTS of 2048
-//               tokens; each segment accumulates in its own TMEM buffer (2 x 256 columns, double buffered) and is
-//               added to the fp32 H in global memory with round-to-nearest while the next segment's MMAs run.
+//               (measured 1.3e-5 relative after 8192 tokens).  The token loop is therefore cut into SEGMENTS; each
+//               segment accumulates in its own TMEM buffer (2 x 256 columns, double buffered) and is drained with
+//               round-to-nearest fp32 adds while the next segment's MMAs run.  Pair kernel: segments of 512 tokens are
+//               summed into a REGISTER-resident running tile (8 epilogue warps x 128 columns per thread), and the fp32
+//               H tile in global memory is read-modify-written ONCE per launch -- 1-CTA kernel: 2048-token segments,
+//               one H round trip per segment.
 //   pipeline    mbarrier full/empty ring of [64 tokens x 64 channels] SWIZZLE_128B boxes: 6 stages x 32 KB per CTA in
 //               pair mode (4 x 48 KB in 1-CTA mode)
 //   warp roles  warp 0 = TMA producer (1 lane), warp 1 = TMEM alloc + MMA issuer (1 lane, even CTA only in pair
@@ -260,6 +263,10 @@ constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;  // 32 KB
 constexpr int SMEM2_BYTES = STAGES2 * STAGE2_BYTES + 1024 + 256;
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;     // shared::cluster address of the even CTA of a pair (cute: Sm100MmaPeerBitMask)
 constexpr int kSuperRows2Default = 8;
+constexpr int EPI2_WARPS = 8;                      // two warps per TMEM lane quarter, 128 columns each
+constexpr int EPI2_THREADS = EPI2_WARPS * 32;
+constexpr int THREADS2 = 64 + EPI2_THREADS;        // TMA warp + MMA warp + epilogue
+constexpr int SEG2_KB = 8;                         // 8 k-blocks of 64 tokens = 512 tokens per TMEM accumulation chain
 
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_even_cta, int c_inner,
                                                  int c_outer) {
@@ -285,8 +292,8 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
-// grid = 2 CTAs per 256 x 256 tile of the super-row enumeration; cluster (2,1,1); block = 192 threads
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// grid = 2 CTAs per 256 x 256 tile of the super-row enumeration; cluster (2,1,1); block = 320 threads
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
     hessian_syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t Ttok, int64_t C, float* __restrict__ H,
                             uint32_t idesc, int super_rows) {
   uint32_t rank;
@@ -324,7 +331,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accum_full(b), 1);
-      mbar_init(accum_empty(b), 2 * NUM_EPI_THREADS);
+      mbar_init(accum_empty(b), 2 * EPI2_THREADS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -358,14 +365,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     }
   } else if (warp == 1) {
     if (lane == 0 && rank == 0) {
-      const int nseg = (nk + SEG_KB - 1) / SEG_KB;
+      const int nseg = (nk + SEG2_KB - 1) / SEG2_KB;
       for (int seg = 0; seg < nseg; ++seg) {
         const int b = seg & 1;
         mbar_wait(accum_empty(b), ((uint32_t)(seg >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + (uint32_t)(b * 256);
-        const int kb1 = min(nk, (seg + 1) * SEG_KB);
-        for (int kb = seg * SEG_KB; kb < kb1; ++kb) {
+        const int kb1 = min(nk, (seg + 1) * SEG2_KB);
+        for (int kb = seg * SEG2_KB; kb < kb1; ++kb) {
           const int s = kb % STAGES2;
           const uint32_t ph = (uint32_t)(kb / STAGES2) & 1u;
           mbar_wait(full_bar(s), ph);
@@ -375,7 +382,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
           for (int k4 = 0; k4 < BK / 16; ++k4) {
             const uint64_t ad = make_desc(sa + k4 * 2048);
             const uint64_t bd = make_desc(sa + A2_BYTES + k4 * 2048);
-            umma_f16_pair(tmem_d, ad, bd, idesc, (kb != seg * SEG_KB || k4 != 0) ? 1u : 0u);
+            umma_f16_pair(tmem_d, ad, bd, idesc, (kb != seg * SEG2_KB || k4 != 0) ? 1u : 0u);
           }
           umma_commit_pair(empty_bar(s));
         }
@@ -383,38 +390,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
       }
     }
   } else {
-    const int q = warp & 3;
+    // epilogue: 8 warps; warp w may touch TMEM lanes [32*(w%4), +32) and owns the column half (w-2)/4 of the tile.
+    // Every 512-token segment is added (round to nearest) into a register-resident running row of 128 columns; the
+    // fp32 H tile is read-modify-written once, after the last segment.
+    const int q = warp & 3, chalf = (warp - 2) >> 2;
     const int64_t row = i0 + q * 32 + lane;
-    const int nseg = (nk + SEG_KB - 1) / SEG_KB;
+    const int nseg = (nk + SEG2_KB - 1) / SEG2_KB;
+    float hacc[128];
+#pragma unroll
+    for (int v = 0; v < 128; ++v) hacc[v] = 0.f;
     for (int seg = 0; seg < nseg; ++seg) {
       const int b = seg & 1;
       mbar_wait(accum_full(b), (uint32_t)(seg >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-      for (int cc = 0; cc < 256 / 32; ++cc) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + cc * 32), r);
-        const int64_t col0 = j0 + cc * 32;
-        if (row < C && col0 < C) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * 256 + chalf * 128 + cc * 32), r);
+#pragma unroll
+        for (int v = 0; v < 32; ++v) hacc[cc * 32 + v] = __fadd_rn(hacc[cc * 32 + v], __uint_as_float(r[v]));
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(accum_empty(b) & kPeerBitMask) : "memory");
+    }
+    if (row < C) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int64_t col0 = j0 + chalf * 128 + cc * 32;
+        if (col0 < C) {
           float* dst = H + row * C + col0;
           if (col0 + 32 <= C && ((C & 3) == 0)) {
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               float4 h = *reinterpret_cast<float4*>(dst + 4 * v);
-              h.x += __uint_as_float(r[4 * v + 0]);
-              h.y += __uint_as_float(r[4 * v + 1]);
-              h.z += __uint_as_float(r[4 * v + 2]);
-              h.w += __uint_as_float(r[4 * v + 3]);
+              h.x += hacc[cc * 32 + 4 * v + 0];
+              h.y += hacc[cc * 32 + 4 * v + 1];
+              h.z += hacc[cc * 32 + 4 * v + 2];
+              h.w += hacc[cc * 32 + 4 * v + 3];
               *reinterpret_cast<float4*>(dst + 4 * v) = h;
             }
           } else {
+#pragma unroll
             for (int v = 0; v < 32; ++v)
-              if (col0 + v < C) dst[v] += __uint_as_float(r[v]);
+              if (col0 + v < C) dst[v] += hacc[cc * 32 + v];
           }
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(accum_empty(b) & kPeerBitMask) : "memory");
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -481,7 +502,7 @@ int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C,
     const int nt = (int)ceil_div(C, 256);
     unsigned tiles = 0;
     for (int ti0 = 0; ti0 < nt; ti0 += super_rows2) tiles += (unsigned)(std::min(super_rows2, nt - ti0) * (nt - ti0));
-    hessian_syrk_tc2_kernel<<<2 * tiles, 192, SMEM2_BYTES, st>>>(tmap, T, C, Hsum, idesc2, super_rows2);
+    hessian_syrk_tc2_kernel<<<2 * tiles, THREADS2, SMEM2_BYTES, st>>>(tmap, T, C, Hsum, idesc2, super_rows2);
     WOQ_LAUNCH_CHECK();
     return 0;
   }
