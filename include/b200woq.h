@@ -221,6 +221,34 @@ int b200woq_mse_accumulate(const void* a, const void* b, int dtype, int64_t coun
 int b200woq_minmax_cols_accumulate(const void* X, int x_dtype, int64_t T, int64_t K, int64_t ldx,
                                    float* mx, float* mn, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * K7  SmoothQuant W8A8 static INT8 linear (smooth_quant/utility.py: SQLinearWrapper :2559-2662,
+ *     quant_dequant_w_v1 :652-690, quant_dequant_x_v1 :726-755; the INT8 GEMM the reference delegates to IPEX)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Padded K of the int8 operands (multiple of 128: one 128-byte swizzle row per pipeline stage). */
+int64_t b200woq_w8a8_padded_k(int64_t K);
+
+/* `sq_smooth` + weight quantisation, once per layer: W' = W * smooth[k] (smooth may be NULL), per-out-channel
+ * symmetric int8: w_scale[n] = max(max_k |W'[n,k]| / 127.5, eps), qweight[n,k] = clamp(rint(W'/w_scale), -128, 127)
+ * written as int8 [N, padded_k(K)] (zero padded), wsum[n] = sum_k qweight[n,k] (int32). */
+int b200woq_sq_smooth_quant_weight(const void* W, int w_dtype, int64_t N, int64_t K, const float* smooth,
+                                   int8_t* qweight, float* w_scale, int32_t* wsum, void* stream);
+
+/* Workspace of b200woq_w8a8_linear_forward: [u8 activation codes M x padded_k | split-K s32 sums + tile counters].
+ * The part from b200woq_w8a8_workspace_zeroed_offset(M, K) on must be ZERO when first used; every call leaves it
+ * zeroed.  256-byte aligned. */
+int64_t b200woq_w8a8_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int64_t b200woq_w8a8_workspace_zeroed_offset(int64_t M, int64_t K);
+
+/* y[M,N] = (sum_k q_x[m,k] q_w[n,k] - zp_x * wsum[n]) * x_scale * w_scale[n] + bias[n]
+ * with q_x = clamp(rint(x * input_scale[k] / x_scale + x_zp), 0, 255) (static per-tensor asym uint8; input_scale
+ * NULL = ones).  x_scale / x_zp are device scalars (fp32; x_zp integer-valued).  tcgen05.mma.kind::i8. */
+int b200woq_w8a8_linear_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, const int8_t* qweight,
+                                const float* w_scale, const int32_t* wsum, const float* input_scale,
+                                const float* x_scale, const float* x_zp, const void* bias, int bias_dtype, void* y,
+                                int y_dtype, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,14 @@ _SIGS = {
     "b200woq_awq_weight_scale": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "b200woq_abs_colsum_accumulate": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "b200woq_mse_accumulate": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    "b200woq_w8a8_padded_k": (c_int64, [c_int64]),
+    "b200woq_sq_smooth_quant_weight": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_void_p]),
+    "b200woq_w8a8_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64]),
+    "b200woq_w8a8_workspace_zeroed_offset": (c_int64, [c_int64, c_int64]),
+    "b200woq_w8a8_linear_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                            c_int64, c_void_p]),
     "b200woq_minmax_cols_accumulate": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                                c_void_p]),
 }

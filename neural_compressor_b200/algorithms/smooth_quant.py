@@ -5,9 +5,9 @@ SQLinearWrapper :2559-2662, quant_dequant_w_v1/x_v1 :652-755, WrapperLayer.q_dq_
 PARITY UNPINNED: the reference module hard-imports intel_extension_for_pytorch and its W8A8 GEMM lives in
 IPEX/oneDNN outside the tree; this row follows the source text and the QDQ simulation only.
 
-Round 1 implements: per-input-channel min/max calibration (kernel), the alpha scale, weight smoothing and a
-`SQLinear` module that applies x*1/s and evaluates the W8A8 QDQ simulation.  The tcgen05 INT8 GEMM is the next
-row (DESIGN.md "what comes next").
+Per-input-channel min/max calibration (stats.cu), the alpha scale, weight smoothing + int8 quantisation
+(b200woq_sq_smooth_quant_weight) and the static W8A8 forward on the tensor cores (b200woq_w8a8_linear_forward,
+tcgen05.mma.kind::i8, w8a8.cu).
 """
 from __future__ import annotations
 
@@ -30,31 +30,44 @@ def cal_scale(input_max_abs, weights, alpha, weight_max_lb=1e-5):
 
 
 class SQLinear(torch.nn.Module):
-    """SQLinearWrapper semantics (utility.py:2559-2662) evaluated as the QDQ simulation (utility.py:2707-2729):
-    x' = x * (1/s); xq = qdq_uint8_per_tensor(x') with static (calibrated) min/max; wq = qdq_int8_per_channel(W*s)."""
+    """SQLinearWrapper (utility.py:2559-2662) as a static W8A8 module on the B200: the smoothing scale is folded into the
+    weight (W' = W * s, `_scale_layer_weight`) and applied to the input as a multiply by `input_scale` = 1/s (:2599-2600);
+    weights are per-out-channel symmetric int8 (`quant_dequant_w_v1`, :652-690), activations static per-tensor asymmetric
+    uint8 from the calibrated range of the smoothed input (`_calculate_qparams`, :2607-2631; `quant_dequant_x_v1`, :726-755).
+    forward = ONE activation-quantisation kernel + ONE tcgen05 `kind::i8` GEMM with the dequant epilogue
+    `(acc - zp_x * sum_k q_w) * s_x * s_w[n] + bias` (ops.w8a8_linear) -- the integer GEMM the reference delegates to IPEX.
+    `forward_qdq` evaluates the reference's pure-torch QDQ simulation (`WrapperLayer.q_dq_forward`, :2707-2729) for
+    cross-checks; it is not used by the product path."""
 
     def __init__(self, linear: torch.nn.Linear, smooth_scale, act_min, act_max):
         super().__init__()
         self.in_features, self.out_features = linear.in_features, linear.out_features
-        w = linear.weight.data.float() * smooth_scale.view(1, -1)
-        eps = torch.finfo(torch.float32).eps
-        w_scale = torch.clip(w.abs().amax(dim=1) / 127.5, min=eps).view(-1, 1)   # utility.py:673-676
-        self.register_buffer("qweight", torch.round(w / w_scale).clamp_(-128, 127).to(torch.int8))
-        self.register_buffer("w_scale", w_scale)
+        dev = linear.weight.device
+        smooth_scale = smooth_scale.to(dev).float().contiguous()
+        r = ops.sq_smooth_quant_weight(linear.weight.data.contiguous(), smooth_scale)
+        self.register_buffer("qweight", r["qweight"])          # int8 [N, padded K]
+        self.register_buffer("w_scale", r["w_scale"])          # fp32 [N]
+        self.register_buffer("wsum", r["wsum"])                # int32 [N]
         self.register_buffer("input_scale", (1.0 / smooth_scale).float())
+        eps = torch.finfo(torch.float32).eps
         # static per-tensor activation qparams from the calibrated range of the SMOOTHED input (:2607-2631)
-        mn = torch.clamp((act_min * self.input_scale).min(), max=0.0)
-        mx = torch.clamp((act_max * self.input_scale).max(), min=0.0)
+        mn = torch.clamp((act_min.to(dev) * self.input_scale).min(), max=0.0)
+        mx = torch.clamp((act_max.to(dev) * self.input_scale).max(), min=0.0)
         x_scale = torch.clip((mx - mn) / 255.0, min=eps)
-        self.register_buffer("x_scale", x_scale.reshape(1))
-        self.register_buffer("x_zp", torch.round((0 - mn) / x_scale).reshape(1))
+        self.register_buffer("x_scale", x_scale.reshape(1).float())
+        self.register_buffer("x_zp", torch.clamp(torch.round((0 - mn) / x_scale), 0, 255).reshape(1).float())
         self.bias = None if linear.bias is None else torch.nn.Parameter(linear.bias.data.clone(), requires_grad=False)
 
     def forward(self, x):
+        return ops.w8a8_linear(x, self.qweight, self.w_scale, self.wsum, self.x_scale, self.x_zp, self.in_features,
+                               input_scale=self.input_scale, bias=None if self.bias is None else self.bias.data)
+
+    def forward_qdq(self, x):
         xs = x.float() * self.input_scale
         q = torch.round(xs / self.x_scale + self.x_zp).clamp_(0, 255)
         xq = self.x_scale * (q - self.x_zp)
-        y = torch.nn.functional.linear(xq, self.qweight.float() * self.w_scale, None if self.bias is None else self.bias.float())
+        w = self.qweight[:, :self.in_features].float() * self.w_scale.view(-1, 1)
+        y = torch.nn.functional.linear(xq, w, None if self.bias is None else self.bias.float())
         return y.to(x.dtype)
 
 

@@ -381,3 +381,62 @@ def minmax_cols_accumulate(X: torch.Tensor, mx: torch.Tensor, mn: torch.Tensor):
     T, K = X2.shape
     check(_lib.load().b200woq_minmax_cols_accumulate(ptr(X2), dt(X2), T, K, K, ptr(mx), ptr(mn), stream_ptr(X.device)),
           "minmax_cols_accumulate")
+
+
+# ------------------------------------------------------------------ K7: SmoothQuant W8A8
+def sq_smooth_quant_weight(W: torch.Tensor, smooth: Optional[torch.Tensor] = None):
+    """W' = W * smooth (per input channel), per-out-channel sym int8 (quant_dequant_w_v1, smooth_quant/utility.py:652-690).
+
+    Returns dict(qweight int8 [N, Kp] zero padded to a multiple of 128, w_scale fp32 [N], wsum int32 [N])."""
+    require_cuda(W, "W")
+    N, K = W.shape
+    lib = _lib.load()
+    Kp = lib.b200woq_w8a8_padded_k(K)
+    qweight = torch.empty((N, Kp), dtype=torch.int8, device=W.device)
+    w_scale = torch.empty(N, dtype=torch.float32, device=W.device)
+    wsum = torch.empty(N, dtype=torch.int32, device=W.device)
+    if smooth is not None:
+        smooth = smooth.float().contiguous()
+    check(lib.b200woq_sq_smooth_quant_weight(ptr(W), dt(W), N, K, ptr(smooth), ptr(qweight), ptr(w_scale), ptr(wsum),
+                                             stream_ptr(W.device)), "sq_smooth_quant_weight")
+    return dict(qweight=qweight, w_scale=w_scale, wsum=wsum)
+
+
+_W8A8_WS = {}
+
+
+def w8a8_linear(x, qweight, w_scale, wsum, x_scale, x_zp, in_features, input_scale=None, bias=None, out_dtype=None):
+    """SQLinearWrapper.forward as a static INT8 GEMM (tcgen05.mma.kind::i8) with the dequant epilogue."""
+    require_cuda(x, "x")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, in_features)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M, K = x2.shape
+    N = qweight.shape[0]
+    lib = _lib.load()
+    if qweight.dtype != torch.int8 or qweight.shape[1] != lib.b200woq_w8a8_padded_k(K) or not qweight.is_contiguous():
+        raise _lib.B200WOQError("qweight must be the contiguous int8 [N, padded_k(K)] tensor of sq_smooth_quant_weight")
+    for t, name, dtp in ((w_scale, "w_scale", torch.float32), (wsum, "wsum", torch.int32), (x_scale, "x_scale", torch.float32),
+                         (x_zp, "x_zp", torch.float32)):
+        if t.dtype != dtp or not t.is_cuda or not t.is_contiguous():
+            raise _lib.B200WOQError(f"{name} must be a contiguous CUDA {dtp} tensor")
+    if input_scale is not None and (input_scale.dtype != torch.float32 or not input_scale.is_contiguous()):
+        raise _lib.B200WOQError("input_scale must be contiguous float32")
+    nbytes = lib.b200woq_w8a8_workspace_bytes(M, N, K)
+    zoff = lib.b200woq_w8a8_workspace_zeroed_offset(M, K)
+    # the split-K tail of the workspace is self-cleaning but must start zeroed: one cached buffer per (device, M, N, K)
+    key = (x.device.index, M, N, K)
+    ws = _W8A8_WS.get(key)
+    if ws is None:
+        if len(_W8A8_WS) > 64:
+            _W8A8_WS.clear()
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=x.device)
+        _W8A8_WS[key] = ws
+    out_dtype = out_dtype or (x.dtype if x.dtype in _lib._DT else torch.float32)
+    y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    check(lib.b200woq_w8a8_linear_forward(ptr(x2), dt(x2), M, K, N, ptr(qweight), ptr(w_scale), ptr(wsum), ptr(input_scale),
+                                          ptr(x_scale), ptr(x_zp), ptr(bias), dt(bias) if bias is not None else 0, ptr(y),
+                                          dt(y), ptr(ws), ws.numel(), stream_ptr(x.device)), "w8a8_linear_forward")
+    assert zoff <= nbytes
+    return y.reshape(*lead, N)

@@ -524,3 +524,28 @@ def sq_qdq_act_per_tensor(x, min_x=None, max_x=None, bits=8):
     bias = torch.round((0 - min_x) / scale)
     q = torch.round(x / scale + bias).clamp_(q_min, q_max)
     return scale * (q - bias), q, scale, bias
+
+
+def sq_w8a8_linear(x, W, smooth, act_min, act_max, bias=None):
+    """`SQLinearWrapper` + the W8A8 QDQ simulation the reference falls back to without IPEX
+    (smooth_quant/utility.py:2559-2662 wrapper, :2607-2631 static activation qparams, :652-690 / :726-755 QDQ,
+    `WrapperLayer.q_dq_forward` :2707-2729), in fp32 torch-CPU ops:
+
+        W' = W * smooth ; x' = x * (1 / smooth)
+        q_w, s_w = per-out-channel sym int8 of W' ; q_x = clamp(round(x' / s_x + zp_x), 0, 255) with the STATIC
+        (calibrated) per-tensor range of x' ; y = (s_x * (q_x - zp_x)) @ (q_w * s_w)^T + bias
+
+    Returns dict(y, q_w int, s_w [N,1], q_x, s_x, zp_x).  PARITY UNPINNED (IPEX absent)."""
+    x, W, smooth = _cpu(x).float(), _cpu(W).float(), _cpu(smooth).float()
+    input_scale = 1.0 / smooth
+    Ws = W * smooth.view(1, -1)
+    _, q_w, s_w = sq_qdq_weight_per_channel(Ws, 8)
+    eps = torch.finfo(torch.float32).eps
+    mn = torch.clamp((_cpu(act_min).float() * input_scale).min(), max=0.0)
+    mx = torch.clamp((_cpu(act_max).float() * input_scale).max(), min=0.0)
+    s_x = torch.clip((mx - mn) / 255.0, min=eps)
+    zp_x = torch.clamp(torch.round((0 - mn) / s_x), 0, 255)
+    xs = x * input_scale
+    q_x = torch.round(xs / s_x + zp_x).clamp_(0, 255)
+    y = torch.nn.functional.linear(s_x * (q_x - zp_x), q_w * s_w, None if bias is None else _cpu(bias).float())
+    return dict(y=y, q_w=q_w, s_w=s_w, q_x=q_x, s_x=s_x, zp_x=zp_x)
