@@ -372,6 +372,7 @@ class RAWGPTQuantizer:
         ent["shared"] = True
 
     def _queue_factor_status(self, infos, block_idx):
+        self._check_factor_status()  # at most one status in flight (true_sequential queues several per block)
         st = torch.stack(infos).max().reshape(1)
         if st.is_cuda:
             host = torch.empty(1, dtype=st.dtype, pin_memory=True)
@@ -427,6 +428,22 @@ class RAWGPTQuantizer:
     def quantize_block(self, block_idx: int):
         blocks = self.blocks_info["transformers"]
         self.rechunk_calibration()
+        self._check_factor_status()
+        # layer-sharded models (utils/sharded.py, BASELINE configs[4]): the block lives on its owner rank only; the owner
+        # broadcasts its weights over NCCL right before the block is processed and the other ranks drop them afterwards
+        shard = getattr(self.model, "_b200_shard", None)
+        fetched = False
+        if shard is not None and shard["world"] > 1:
+            from ..utils import sharded
+
+            owner = sharded.block_owner(block_idx, shard["world"], shard["n_blocks"])
+            t_f = time.perf_counter()
+            nbytes = sharded.fetch_block(blocks[block_idx], owner, self.device)
+            fetched = owner != shard["rank"]
+            self.fetch_stats = getattr(self, "fetch_stats", [])
+            if self.profile:
+                torch.cuda.synchronize()
+            self.fetch_stats.append((block_idx, nbytes, time.perf_counter() - t_f))
         block = blocks[block_idx].to(self.device)
         sub_layers = find_layers(block)
         for sequential in self._sequentials(block):
@@ -561,7 +578,6 @@ class RAWGPTQuantizer:
             # factorisation status of this group's Hessians: the reference's torch.linalg.cholesky raises on a
             # non-positive-definite H (gptq.py:1228).  The status is copied to pinned host memory asynchronously and
             # examined when the NEXT block starts (or at the end of the run), so no block ever waits on the host.
-            self._check_factor_status()
             if infos:
                 self._queue_factor_status(infos, block_idx)
             t0 = self._sync_time("propagate", t0)
@@ -581,6 +597,14 @@ class RAWGPTQuantizer:
                                        g_idx=r.get("perm"))
                 set_module(block, lname, new_module)
             self._sync_time("pack", t0)
+        if fetched:
+            # not ours: the owner keeps the packed block, this rank only needed it for its share of the calibration
+            from ..utils import sharded
+
+            # (stream-safe without a host sync: the weights were allocated on the main stream and every side stream that
+            # read them has been joined into it before forward #2 was queued)
+            blocks[block_idx] = sharded.release_block(block)
+            return blocks[block_idx]
         if self.offload_packed_to_host:
             block = block.to("cpu")
             blocks[block_idx] = block

@@ -14,7 +14,7 @@
 //   precision   the tensor core adds into its fp32 accumulator with truncation, so a long contraction drifts
 //               (measured 1.3e-5 relative after 8192 tokens).  The token loop is therefore cut into SEGMENTS; each
 //               segment accumulates in its own TMEM buffer (2 x 256 columns, double buffered) and is drained with
-//               round-to-nearest fp32 adds while the next segment's MMAs run.  Pair kernel: segments of 512 tokens are
+//               round-to-nearest fp32 adds while the next segment's MMAs run.  Pair kernel: segments of 256 tokens are
 //               summed into a REGISTER-resident running tile (8 epilogue warps x 128 columns per thread), and the fp32
 //               H tile in global memory is read-modify-written ONCE per launch -- 1-CTA kernel: 2048-token segments,
 //               one H round trip per segment.
@@ -266,7 +266,7 @@ constexpr int kSuperRows2Default = 8;
 constexpr int EPI2_WARPS = 8;                      // two warps per TMEM lane quarter, 128 columns each
 constexpr int EPI2_THREADS = EPI2_WARPS * 32;
 constexpr int THREADS2 = 64 + EPI2_THREADS;        // TMA warp + MMA warp + epilogue
-constexpr int SEG2_KB = 8;                         // 8 k-blocks of 64 tokens = 512 tokens per TMEM accumulation chain
+constexpr int kSeg2KbDefault = 4;                  // k-blocks of 64 tokens per TMEM accumulation chain (256 tokens)
 
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_even_cta, int c_inner,
                                                  int c_outer) {
@@ -295,7 +295,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // grid = 2 CTAs per 256 x 256 tile of the super-row enumeration; cluster (2,1,1); block = 320 threads
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS2, 1)
     hessian_syrk_tc2_kernel(const __grid_constant__ CUtensorMap tmap, int64_t Ttok, int64_t C, float* __restrict__ H,
-                            uint32_t idesc, int super_rows) {
+                            uint32_t idesc, int super_rows, int SEG2_KB) {
   uint32_t rank;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
   int id = blockIdx.x >> 1, ti0 = 0, rows;
@@ -502,7 +502,10 @@ int hessian_accumulate_tcgen05(const void* X, int x_dtype, int64_t T, int64_t C,
     const int nt = (int)ceil_div(C, 256);
     unsigned tiles = 0;
     for (int ti0 = 0; ti0 < nt; ti0 += super_rows2) tiles += (unsigned)(std::min(super_rows2, nt - ti0) * (nt - ti0));
-    hessian_syrk_tc2_kernel<<<2 * tiles, THREADS2, SMEM2_BYTES, st>>>(tmap, T, C, Hsum, idesc2, super_rows2);
+    // shorter TMEM accumulation chains = less truncation bias in H (the tensor core adds with truncation); the epilogue
+    // warps drain each chain into registers while the next one runs
+    static const int seg_kb = getenv("B200WOQ_SYRK_SEG_KB") ? std::max(1, atoi(getenv("B200WOQ_SYRK_SEG_KB"))) : kSeg2KbDefault;
+    hessian_syrk_tc2_kernel<<<2 * tiles, THREADS2, SMEM2_BYTES, st>>>(tmap, T, C, Hsum, idesc2, super_rows2, seg_kb);
     WOQ_LAUNCH_CHECK();
     return 0;
   }

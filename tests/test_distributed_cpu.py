@@ -145,3 +145,50 @@ def test_row_sharded_fasterquant_is_exact_gloo_world2():
     port = 29712 + os.getpid() % 200
     mp.spawn(_rows_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _sharded_worker(rank, world, port, ret):
+    """Layer-sharded model (utils/sharded.py): every rank builds the same model but only its own blocks have storage; the
+    owner's broadcast reproduces the block bit-exactly on the other rank, which drops it again afterwards."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    from neural_compressor_b200.utils import sharded
+
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=4, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=100, max_position_embeddings=64)
+    m = sharded.build_layer_sharded(lambda: LlamaForCausalLM(cfg), "model.layers", rank, world, "cpu")
+    full = sharded.build_layer_sharded(lambda: LlamaForCausalLM(cfg), "model.layers", 0, 1, "cpu")  # the whole model
+    layers = m.model.layers
+    lo, hi = sharded.block_range(rank, world, 4)
+    ok = [sharded.is_remote(b) for b in layers] == [not (lo <= i < hi) for i in range(4)]
+    ok = ok and torch.equal(m.model.embed_tokens.weight, full.model.embed_tokens.weight)
+    ids = torch.randint(0, 100, (1, 8), generator=torch.Generator().manual_seed(1))
+    h = full.model.embed_tokens(ids)
+    pos = full.model.rotary_emb(h, torch.arange(8)[None])
+    for i in range(4):
+        owner = sharded.block_owner(i, world, 4)
+        nbytes = sharded.fetch_block(layers[i], owner, "cpu")
+        ok = ok and nbytes > 0 and not sharded.is_remote(layers[i])
+        for (n1, p1), (n2, p2) in zip(layers[i].named_parameters(), full.model.layers[i].named_parameters()):
+            ok = ok and n1 == n2 and torch.equal(p1, p2)
+        a = layers[i](h, position_embeddings=pos)
+        b = full.model.layers[i](h, position_embeddings=pos)
+        a, b = (a if isinstance(a, torch.Tensor) else a[0]), (b if isinstance(b, torch.Tensor) else b[0])
+        ok = ok and torch.equal(a, b)
+        h = b
+        if owner != rank:
+            layers[i] = sharded.release_block(layers[i])
+            ok = ok and sharded.is_remote(layers[i])
+    ret[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_layer_sharded_model_fetch_release_gloo_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 30112 + os.getpid() % 200
+    mp.spawn(_sharded_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}

@@ -54,7 +54,7 @@ def _cmp(out, exp_codes, ref):
 def test_gptq_parity_at_baseline_shapes(tag, N, C, blocksizes, parity_log):
     from neural_compressor_b200 import ops
 
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(os.cpu_count(), 32))
     W, X = _make(N, C, seed=N + C)
     t0 = time.perf_counter()
     lay = O.GPTQLayerOracle(N, C, bits=4, sym=True)
@@ -62,6 +62,9 @@ def test_gptq_parity_at_baseline_shapes(tag, N, C, blocksizes, parity_log):
         lay.add_batch(x)
     H_o = lay.H.clone()
     _, Hinv_o, _ = lay.prepare_hinv(W.float(), 0.01)
+    # the column loop is thousands of tiny torch ops: more threads only add fork/join overhead (320 s with 128 threads
+    # vs seconds with 16 on the GPU box)
+    torch.set_num_threads(min(os.cpu_count(), 16))
     refs = {bs: lay.fasterquant(W.float(), bs, 0.01, 128, hinv=Hinv_o) for bs in blocksizes}
     exp = {bs: _codes(refs[bs]) for bs in blocksizes}
     t_oracle = time.perf_counter() - t0
@@ -103,6 +106,7 @@ def test_gptq_parity_at_baseline_shapes(tag, N, C, blocksizes, parity_log):
     swaps["oracle_Hinv__cuda_K3"] = _cmp(out, exp[bs], refs[bs])             # column loop + lazy GEMM only
     out = ops.gptq_fasterquant(Wd.clone(), ops.cholesky_inverse_upper(H_o_d.to(DEV).contiguous()), dead, bs, 128, 4, True, False)
     swaps["oracle_H__cuda_K2_K3"] = _cmp(out, exp[bs], refs[bs])             # + our inverse factor
+    torch.set_num_threads(min(os.cpu_count(), 32))
     Hinv_mix = O.GPTQLayerOracle.cholesky_inverse_upper(H.cpu())
     out = ops.gptq_fasterquant(Wd.clone(), Hinv_mix.to(DEV).contiguous(), dead, bs, 128, 4, True, False)
     swaps["cuda_K1__oracle_chain__cuda_K3"] = _cmp(out, exp[bs], refs[bs])   # our Hessian, LAPACK chain
