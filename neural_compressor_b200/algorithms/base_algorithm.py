@@ -32,6 +32,9 @@ class Quantizer(ABC):
         return self.convert(model, *args, **kwargs)
 
     def execute(self, model: torch.nn.Module, mode, *args: Any, **kwargs: Any):
+        # compared by VALUE: when the entries are registered into the reference's own registry the
+        # reference passes ITS `Mode` enum (common/utils/constants.py:55-62), a different class with the same values
+        mode = Mode(getattr(mode, "value", mode))
         if mode == Mode.PREPARE:
             return self.prepare(model, *args, **kwargs)
         if mode == Mode.CONVERT:

@@ -211,7 +211,10 @@ class RAWGPTQuantizer:
 
         for emb in self.blocks_info["embeddings"].values():
             emb.to(self.device)
-        blocks[0] = blocks[0].to(self.device)
+        # (a layer-sharded model may hold block 0 as a storage-less skeleton on this rank: only its forward is
+        # intercepted here, its weights arrive with the owner's broadcast in quantize_block)
+        if not any(p.is_meta for p in blocks[0].parameters()):
+            blocks[0] = blocks[0].to(self.device)
         self._block0_forward = blocks[0].forward
         blocks[0].forward = partial(capture, blocks[0])
         self._model_forward = self.model.forward

@@ -63,6 +63,7 @@ def get_quantizer(model, quantizer_cls, quant_config=None, *args, **kwargs):
 
 def postprocess_model(model, mode, quantizer):
     """utility.py:184-201."""
+    mode = Mode(getattr(mode, "value", mode))  # the reference's own Mode enum is accepted too (same values)
     if mode == Mode.PREPARE:
         model.quantizer = quantizer
     elif mode in (Mode.CONVERT, Mode.QUANTIZE):
