@@ -183,7 +183,9 @@ int64_t b200woq_gptq_workspace_bytes(int64_t N, int64_t C, int blocksize);
  *   scale/zero fp32 [N,G], G = ceil(C/groupsize) (groupsize<=0 => 1 group = per-channel)
  *   losses fp32 [N] per-row sum of (w-q)^2/d^2/2 (gptq.py:1294,1303,1318) (may be NULL)
  * blocksize must be a multiple of groupsize (or groupsize<=0) -- the find_params "stale view"
- * semantics of blocksize > groupsize are reproduced.  flags bit0: mse search.
+ * semantics of blocksize > groupsize are reproduced.  flags bit0: mse search; bit1: double
+ * quantisation of each group's scales over the output rows (gptq.py:1598-1614) with bit2 = symmetric, bits 8-15 =
+ * double_quant_bits, bits 16-31 = double_quant_group_size.
  * The lazy update W[:, i2:] -= Err1 @ Hinv[i1:i2, i2:] (gptq.py:1304) runs as exact fp32 FFMA tiles by default. */
 int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8_t* dead_mask, int64_t N, int64_t C,
                              int blocksize, int groupsize, int bits, int sym, int flags, uint8_t* codes, float* Q,

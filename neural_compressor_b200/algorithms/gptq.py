@@ -320,13 +320,15 @@ class RAWGPTQuantizer:
 
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         N = W.shape[0]
-        if world == 1 or N % world != 0:
+        dq = self._double_quant(cfg)
+        # double quant groups the scales over consecutive output rows: shards must not cut a group
+        if world == 1 or N % world != 0 or (dq is not None and (N // world) % dq["group_size"] != 0):
             return ops.gptq_fasterquant(W, Hinv, dead, cfg["block_size"], cfg["group_size"], cfg["bits"], cfg["sym"],
-                                        cfg["mse"])
+                                        cfg["mse"], double_quant=self._double_quant(cfg))
         rank = dist.get_rank()
         rows = N // world
         part = ops.gptq_fasterquant(W[rank * rows:(rank + 1) * rows].contiguous(), Hinv, dead, cfg["block_size"],
-                                    cfg["group_size"], cfg["bits"], cfg["sym"], cfg["mse"], want_q=False)
+                                    cfg["group_size"], cfg["bits"], cfg["sym"], cfg["mse"], want_q=False, double_quant=dq)
         out = {}
         for k in ("codes", "scale", "zero", "losses"):
             v = part[k]
@@ -335,6 +337,13 @@ class RAWGPTQuantizer:
             out[k] = full
         out["Q"] = ops.gptq_rebuild_q(out["codes"], out["scale"], out["zero"], cfg["group_size"])
         return out
+
+    @staticmethod
+    def _double_quant(cfg):
+        if not cfg.get("use_double_quant"):
+            return None
+        return dict(bits=int(cfg.get("double_quant_bits", 8)), group_size=int(cfg.get("double_quant_group_size", 256)),
+                    sym=bool(cfg.get("double_quant_sym", False)))
 
     def _global_nsamples(self, local_n: int) -> int:
         """Sum of the ranks' sample counts.  Every block sees the same calibration set, so the (synchronising) all-reduce
@@ -508,8 +517,16 @@ class RAWGPTQuantizer:
                     (float(cfg["percdamp"]), bool(cfg["act_order"])))
             for lname, layer in layers.items():
                 cfg = self.get_layer_config(self.full_name(lname, block_idx))
-                if cfg.get("static_groups") or cfg.get("hybrid_order") or cfg.get("fp8_aware") or cfg.get("use_double_quant"):
-                    raise NotImplementedError("static_groups / hybrid_order / fp8_aware / double quant: SURVEY §8 f3")
+                if cfg.get("static_groups") and cfg["group_size"] not in (-1, layer.weight.shape[-1]):
+                    # the reference itself cannot run this: with static_groups its fasterquant returns ONE scale column
+                    # (gptq.py:1193-1200 skips the per-group append, :1339-1341 appends the last quantizer only) and the
+                    # export then raises IndexError (utility.py:483-537 indexes scale[:, i]); verified on the live reference
+                    raise NotImplementedError("static_groups with group_size < in_features: the reference raises "
+                                              "IndexError at export (gptq.py:1339-1341); nothing to be drop-in for")
+                if cfg.get("hybrid_order") or cfg.get("fp8_aware"):
+                    raise NotImplementedError("hybrid_order / fp8_aware are HPU (Gaudi) paths of the reference: out of scope")
+                if cfg.get("use_double_quant") and str(cfg.get("double_quant_dtype", "int")) != "int":
+                    raise NotImplementedError("double quant of scales: int dtype only")
                 slot = bank.layer_to_slot[lname]
                 key = (slot, float(cfg["percdamp"]), bool(cfg["act_order"]))
                 if key in by_slot:

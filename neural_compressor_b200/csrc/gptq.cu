@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "rtn_math.cuh"
 
 namespace b200woq {
 
@@ -114,6 +115,39 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) {
       scale[n * G + gi0 + gl] = s;
       zero[n * G + gi0 + gl] = z;
+    }
+  }
+}
+
+// Quantizer.find_params with use_double_quant (gptq.py:1598-1614): the freshly computed scales of one group, taken as the
+// vector [1, N] over the output rows, are fake-quantised by quant_tensor(dtype int, bits, group_size, scheme, quantile=1,
+// return_int=False, full_range=False): consecutive `dq_g` rows form a group (ragged tail = its own group).
+// One warp per (weight group, row chunk).
+__global__ void __launch_bounds__(256)
+    gptq_double_quant_kernel(float* __restrict__ scale, int64_t N, int64_t G, int64_t gi0, int ngroups, int dq_bits, int dq_g,
+                             int dq_sym) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t chunks = (N + dq_g - 1) / dq_g;
+  const QRange r = qrange(dq_bits, dq_sym != 0);
+  for (int64_t task = warp; task < chunks * ngroups; task += nwarps) {
+    const int64_t ch = task / ngroups, gi = gi0 + task % ngroups;
+    const int64_t n0 = ch * dq_g, n1 = (n0 + dq_g < N) ? n0 + dq_g : N;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int64_t n = n0 + lane; n < n1; n += 32) {
+      const float v = scale[n * G + gi];
+      mn = fminf(mn, v);
+      mx = fmaxf(mx, v);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    float s, z;
+    rtn_group_params<float>(mn, mx, dq_bits, dq_sym != 0, false, 1.0f, s, z);
+    for (int64_t n = n0 + lane; n < n1; n += 32) {
+      float q = rtn_code<float>(scale[n * G + gi], s, z, dq_sym != 0, r);
+      if (!dq_sym) q = __fsub_rn(q, z);
+      scale[n * G + gi] = __fmul_rn(q, s);
     }
   }
 }
@@ -479,12 +513,19 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
   const int g = per_channel ? (int)C : groupsize;
   const int64_t G = per_channel ? 1 : ceil_div(C, g);
   const int mse = flags & 1;
+  // flags bit 1: double quantisation of the scales; bit 2: symmetric; bits 8-15: bits; bits 16-31: group size
+  const int dq = (flags >> 1) & 1, dq_sym = (flags >> 2) & 1, dq_bits = (flags >> 8) & 0xff, dq_g = (flags >> 16) & 0xffff;
+  WOQ_CHECK_ARG(!dq || (dq_bits >= 1 && dq_bits <= 8 && dq_g > 0), "gptq_fasterquant: bad double-quant parameters");
   if (losses) WOQ_CUDA(cudaMemsetAsync(losses, 0, sizeof(float) * N, st));
   const int fp_blocks = (int)std::min<int64_t>(ceil_div(N * 32, 256) * 4, (int64_t)num_sms() * 8);
 
   if (per_channel) {  // gptq.py:1184-1185: one find_params over the whole row, BEFORE dead columns are zeroed
     gptq_find_params_kernel<<<fp_blocks, 256, 0, st>>>(W, N, C, 0, (int)C, 0, 1, 1, maxq, sym, mse, scale, zero);
     WOQ_LAUNCH_CHECK();
+    if (dq) {
+      gptq_double_quant_kernel<<<fp_blocks, 256, 0, st>>>(scale, N, 1, 0, 1, dq_bits, dq_g, dq_sym);
+      WOQ_LAUNCH_CHECK();
+    }
   }
   if (dead_mask) {  // gptq.py:1191  W[:, dead] = 0
     zero_dead_columns_kernel<<<fp_blocks, 256, 0, st>>>(W, N, C, dead_mask);
@@ -501,6 +542,11 @@ extern "C" int b200woq_gptq_fasterquant(float* W, const float* Hinv, const uint8
         gptq_find_params_kernel<<<fp_blocks, 256, 0, st>>>(W, N, C, gfirst * g, g, gfirst, (int)(glast - gfirst + 1), G,
                                                            maxq, sym, mse, scale, zero);
         WOQ_LAUNCH_CHECK();
+        if (dq) {
+          gptq_double_quant_kernel<<<fp_blocks, 256, 0, st>>>(scale, N, G, gfirst, (int)(glast - gfirst + 1), dq_bits, dq_g,
+                                                              dq_sym);
+          WOQ_LAUNCH_CHECK();
+        }
       }
     }
     for (int64_t c0 = i1; c0 < i2; c0 += SUB) {

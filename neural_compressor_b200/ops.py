@@ -307,8 +307,11 @@ def cholesky_inverse_upper(H: torch.Tensor, info: Optional[torch.Tensor] = None,
 
 
 def gptq_fasterquant(W: torch.Tensor, Hinv: torch.Tensor, dead_mask: Optional[torch.Tensor], blocksize=128,
-                     groupsize=-1, bits=4, sym=False, mse=False, want_q=True):
+                     groupsize=-1, bits=4, sym=False, mse=False, want_q=True, double_quant=None):
     """GPTQ.fasterquant column loop for one layer (gptq.py:1250-1304).  W fp32 [N,C] is destroyed.
+
+    `double_quant` = None or dict(bits, group_size, sym): fake-quantise each group's scales over the output rows
+    (Quantizer.find_params with use_double_quant, gptq.py:1598-1614).
 
     Returns dict(codes uint8 [N,C], Q fp32 [N,C] | None, scale [N,G], zero [N,G], losses [N])."""
     require_cuda(W, "W")
@@ -324,8 +327,12 @@ def gptq_fasterquant(W: torch.Tensor, Hinv: torch.Tensor, dead_mask: Optional[to
     lib = _lib.load()
     nbytes = lib.b200woq_gptq_workspace_bytes(N, C, blocksize)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    flags = 1 if mse else 0
+    if double_quant:
+        flags |= 2 | (4 if double_quant.get("sym") else 0) | (int(double_quant.get("bits", 8)) << 8) | \
+            (int(double_quant.get("group_size", 256)) << 16)
     check(lib.b200woq_gptq_fasterquant(ptr(W), ptr(Hinv), ptr(dead_mask), N, C, blocksize, groupsize, bits, int(sym),
-                                       1 if mse else 0, ptr(codes), ptr(Q), ptr(scale), ptr(zero), ptr(losses),
+                                       flags, ptr(codes), ptr(Q), ptr(scale), ptr(zero), ptr(losses),
                                        ptr(ws), nbytes, stream_ptr(dev)), "gptq_fasterquant")
     return dict(codes=codes, Q=Q, scale=scale, zero=zero, losses=losses)
 

@@ -331,6 +331,43 @@ def gen_options():
     torch.save(out, os.path.join(OUT, "options_matrix.pt"))
 
 
+EXTRA_CASES = [
+    # f3 leftovers (round 2): double quantisation of the GPTQ scales (gptq.py:1598-1614)
+    ("gptq_double_quant", "gptq", dict(bits=4, group_size=32, use_sym=True, block_size=128, use_double_quant=True)),
+    ("gptq_double_quant_sym_g64", "gptq", dict(bits=4, group_size=32, use_sym=False, block_size=128, use_double_quant=True,
+                                               double_quant_use_sym=True, double_quant_group_size=64)),
+]
+
+
+def gen_options_extra():
+    """Round-2 additions to the option matrix, in their own fixture (tests/golden/options_extra.pt), plus the recorded
+    behaviour of the reference for `static_groups=True` (it raises IndexError at export)."""
+    from neural_compressor.torch.quantization import GPTQConfig, convert, prepare
+
+    ids = calib_ids()
+    probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
+    out = dict(cases={})
+    for tag, algo, kw in EXTRA_CASES:
+        m = tiny_llama()
+        m = prepare(m, GPTQConfig(model_path="/tmp", **kw))
+        for x in ids:
+            m(x)
+        m = convert(m)
+        with torch.no_grad():
+            out["cases"][tag] = dict(algo=algo, kw=kw, state=woq_state(m), logits=m(probe).logits.clone())
+        print("options_extra:", tag)
+    try:
+        m = prepare(tiny_llama(), GPTQConfig(bits=4, group_size=32, static_groups=True, model_path="/tmp"))
+        for x in ids:
+            m(x)
+        convert(m)
+        out["static_groups_reference"] = "ok"
+    except Exception as ex:  # the reference cannot run its own option (gptq.py:1339-1341 -> utility.py:483-537)
+        out["static_groups_reference"] = f"{type(ex).__name__}: {ex}"
+    print("static_groups in the reference:", out["static_groups_reference"])
+    torch.save(out, os.path.join(OUT, "options_extra.pt"))
+
+
 def gen_hf_config():
     """AutoGPTQ-style quantization_config the reference derives from a config mapping (save_load.py:1094-1156)."""
     import json
@@ -354,6 +391,8 @@ def gen_hf_config():
     print("hf_config:", cases)
 
 
+GENERATORS_EXTRA = {"options_extra": gen_options_extra}
+
 if __name__ == "__main__":
     load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -373,3 +412,5 @@ if __name__ == "__main__":
             gen_hf_config()
         if "options" in which:
             gen_options()
+        if "options_extra" in which:
+            gen_options_extra()

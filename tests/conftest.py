@@ -92,3 +92,8 @@ def golden_e2e():
 @pytest.fixture(scope="session")
 def golden_options():
     return load_golden("options_matrix.pt")
+
+
+@pytest.fixture(scope="session")
+def golden_options_extra():
+    return load_golden("options_extra.pt")

@@ -129,11 +129,33 @@ def test_rtn_conv1d_model_bit_exact(api, golden_options):
     assert (logits - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
 
 
-@pytest.mark.parametrize("kw", [dict(static_groups=True), dict(use_double_quant=True)])
-def test_unsupported_gptq_options_raise(api, golden_e2e, kw):
-    """Options outside the B200 hot path fail loudly instead of silently quantising differently."""
+@pytest.mark.parametrize("tag", ["gptq_double_quant", "gptq_double_quant_sym_g64"])
+def test_gptq_double_quant(api, golden_e2e, golden_options_extra, tag, parity_log):
+    """use_double_quant: each group's scales are fake-quantised over the output rows (gptq.py:1598-1614), against the
+    packed tensors of the live reference (tests/golden/options_extra.pt)."""
+    case = golden_options_extra["cases"][tag]
     m = tiny_llama(golden_e2e["init_state"]).to(DEV)
-    m = api.prepare(m, api.GPTQConfig(bits=4, group_size=32, **kw))
+    m = api.prepare(m, api.GPTQConfig(**case["kw"]))
+    for x in golden_e2e["ids"]:
+        m(x.to(DEV))
+    m = api.convert(m)
+    worst = compare(m, case["state"], bits_of(case["kw"]), exact=False)
+    parity_log(f"options/{tag}", worst)
+    assert worst["code"] <= 3e-2 and worst["scale"] <= 1e-3 and worst["zero"] <= 3e-2, worst
+    # the double-quantised scales take few distinct values per 256-row group: compare the layer-0 scales exactly-ish
+    with torch.no_grad():
+        logits = m(golden_e2e["probe"].to(DEV)).logits.float().cpu()
+    ref = case["logits"]
+    assert (logits - ref).abs().max().item() < 5e-2 * ref.abs().max().item()
+
+
+def test_static_groups_matches_the_reference_failure(api, golden_e2e, golden_options_extra):
+    """`static_groups=True` with group_size < in_features cannot run in the reference either: its fasterquant returns a
+    single scale column (gptq.py:1193-1200, 1339-1341) and the export raises IndexError (recorded from the live reference
+    in the fixture).  We fail loudly at the same place instead of quantising differently."""
+    assert golden_options_extra["static_groups_reference"].startswith("IndexError")
+    m = tiny_llama(golden_e2e["init_state"]).to(DEV)
+    m = api.prepare(m, api.GPTQConfig(bits=4, group_size=32, static_groups=True))
     for x in golden_e2e["ids"][:2]:
         m(x.to(DEV))
     with pytest.raises(NotImplementedError):
