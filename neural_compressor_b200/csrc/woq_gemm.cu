@@ -26,6 +26,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include <cstdlib>
 
 namespace b200woq {
 
@@ -578,8 +579,26 @@ static size_t fast_smem_bytes(int64_t Mc, int mt, int64_t gmax, int g, int bits)
 
 using namespace b200woq;
 
-extern "C" int64_t b200woq_linear_workspace_bytes(int64_t, int64_t, int64_t, int, int) {
-  return 256;  // split-K partials live in distributed shared memory; no global scratch is needed any more
+namespace b200woq {
+// woq_tc.cu: tcgen05 dequant-GEMM for batches of 9..128 rows
+bool woq_tc_shape_ok(int64_t M, int64_t N, int64_t K, int bits, int g, const int32_t* g_idx);
+int64_t woq_tc_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, const int32_t* qweight, const int32_t* qzeros,
+                   const __half* scales, const void* bias, int bias_dtype, const float* input_scale, void* y, int y_dtype,
+                   int g, void* workspace, int64_t workspace_bytes, int pdl, cudaStream_t st);
+}  // namespace b200woq
+
+static int tc_min_rows() {
+  static const int v = getenv("B200WOQ_TC_MIN_ROWS") ? atoi(getenv("B200WOQ_TC_MIN_ROWS")) : 9;
+  return v;
+}
+
+// The cluster kernel keeps its split-K partials in distributed shared memory; the tensor-core kernel (9..128 rows) needs
+// tile counters (zero on first use, left zero) + fp32 partial tiles in global memory.
+extern "C" int64_t b200woq_linear_workspace_bytes(int64_t M, int64_t N, int64_t K, int bits, int group_size) {
+  const int g = eff_group(K, group_size);
+  if (M >= tc_min_rows() && woq_tc_shape_ok(M, N, K, bits, g, nullptr)) return woq_tc_workspace_bytes(M, N, K);
+  return 256;
 }
 
 template <int BITS>
@@ -666,6 +685,10 @@ extern "C" int b200woq_linear_forward(const void* x, int x_dtype, int64_t M, int
   p.G = ceil_div(K, g);
   p.pdl = (flags & 2) ? 1 : 0;
   const size_t xes = x_dtype == B200WOQ_F32 ? 4 : 2, yes = y_dtype == B200WOQ_F32 ? 4 : 2;
+  if (!(flags & 1) && x_dtype == B200WOQ_F16 && M >= tc_min_rows() && woq_tc_shape_ok(M, N, K, bits, g, g_idx) && workspace &&
+      workspace_bytes >= woq_tc_workspace_bytes(M, N, K))
+    return woq_tc_forward(x, x_dtype, M, K, N, qweight, qzeros, (const __half*)scales16, bias, bias_dtype, input_scale, y,
+                          y_dtype, g, workspace, workspace_bytes, p.pdl, st);
   const bool fast = !(flags & 1) && fast_path_ok(N, K, bits, g, g_idx);
   if (!fast) {
     p.x = x;

@@ -360,7 +360,7 @@ struct PParams {
 constexpr int kSlots = 4;  // strip segments a warp's record range may touch
 
 template <int MODE, int NI_T>
-__global__ void __launch_bounds__(512) woq_gemm_persist_kernel(const PParams p) {
+__global__ void __launch_bounds__(1024) woq_gemm_persist_kernel(const PParams p) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, t = lane & 3;
@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(512) woq_gemm_persist_kernel(const PParams p) 
   float* xsum = reinterpret_cast<float*>(xs + (size_t)p.M * p.xs_ld);
   float* slots = xsum + (((size_t)p.M * G + 3) & ~(size_t)3);                  // [W][kSlots][M][32]
   int* seg_first = reinterpret_cast<int*>(slots + (size_t)W * kSlots * p.M * 32);  // [W] first local strip, [W] count
-  __half* zpad = reinterpret_cast<__half*>(seg_first + 2 * W);
+  __half* zpad = reinterpret_cast<__half*>(seg_first + ((2 * W + 3) & ~3));  // keep the 16-byte alignment
 
   const uint8_t* src = p.recs + ((size_t)s0 * G + wa) * rec_bytes;
   if (lane == 0) {
@@ -680,7 +680,7 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
     const int max_strips = (int)ceil_div(q.n_strips, ctas);
     static const int env_w = getenv("B200WOQ_PERSIST_WARPS") ? atoi(getenv("B200WOQ_PERSIST_WARPS")) : 16;
     static const int env_n = getenv("B200WOQ_PERSIST_NST") ? atoi(getenv("B200WOQ_PERSIST_NST")) : 0;
-    int Wp = std::max(1, std::min(env_w, 16));
+    int Wp = std::max(1, std::min(env_w, 32));
     const int rec_b = q.NI * 512 + 96;
     // every warp needs work, and its contiguous range may touch at most kSlots strips
     while (Wp > 1 && (int64_t)max_strips * q.G < 2ll * Wp) Wp /= 2;
@@ -690,7 +690,7 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
       b += ((size_t)w * n * 8 + 127) & ~(size_t)127;
       b += (size_t)q.M * q.xs_ld * 2;
       b += (((size_t)q.M * q.G + 3) & ~(size_t)3) * 4;
-      b += (size_t)w * kSlots * q.M * 32 * 4 + (size_t)2 * w * 4 + (size_t)(g + 32) * 2;
+      b += (size_t)w * kSlots * q.M * 32 * 4 + (size_t)((2 * w + 3) & ~3) * 4 + (size_t)(g + 32) * 2;
       return (b + 127) & ~(size_t)127;
     };
     const size_t half_sm = (size_t)(227 * 1024) / 2 - 1024, full_sm = 226 * 1024;

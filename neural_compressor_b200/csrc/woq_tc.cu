@@ -1,0 +1,476 @@
+// woq_tc.cu -- K6 for batches of 9..128 rows: INT4 group-wise dequant-GEMM on the 5th-generation tensor cores.
+//   reference: INCWeightOnlyLinear.forward (modules.py:594-610): recover() = fp16(int8(q - zp) * scale_fp16), F.linear.
+//
+// Out-channels are MMA-M (128 per CTA), batch rows are MMA-N (16..128), so small batches waste no tensor rows and the
+// kernel stays HBM-bound on the packed weights.  Per CTA (448 threads, warp-specialised):
+//   warp 0        TMA producer: [8 k-words x 128 out-channels] int32 boxes of the reference's OPTIMUM-format `qweight`
+//                 (no derived layout: word (kw, n) already holds 8 consecutive k of out-channel n) -> 8-stage smem ring
+//   warps 2-5,    two dequant groups (alternate 64-k blocks), one thread per out-channel row: 8 LDS.32 -> per word
+//   warps 6-9     1 SHF + 4 LOP3 ((w & mask) | magic: fp16 1024+q / 64+q) + 4 HSUB2 (exact q - zp) + 4 HMUL2 (one rounding
+//                 = the reference's fp16 weight, bit for bit) -> tcgen05.st: the dequantised A tile goes straight into
+//                 TENSOR MEMORY (128 lanes x 32 columns per 64-k block), never through shared memory -- writing fp16
+//                 weights (4x the packed bytes) to smem and reading them back would cap the kernel near 45 % of HBM
+//   warps 10-13   activation staging: x tile [batch x 64 k] -> fp16, k permuted [0,4,1,5,2,6,3,7] per 8 (the order the
+//                 LOP3 extraction yields), K-major SWIZZLE_128B smem tile (B operand); afterwards the epilogue:
+//                 tcgen05.ld of D[128 x batch] fp32 -> (+bias) -> y, coalesced over out-channels
+//   warp 1        MMA issuer: tcgen05.mma.kind::f16 with A from TMEM, B from smem, D fp32 in TMEM; tcgen05.commit frees
+//                 the A / B stages
+// Split-K over gridDim.y when the tile grid is smaller than the chip: fp32 partial tiles go to a workspace and the LAST
+// CTA of a tile (atomic counter, self-resetting) sums them in fixed split order -> deterministic.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace b200woq {
+namespace woqtc {
+
+constexpr int TMN = 128;     // out-channels per CTA (MMA M)
+constexpr int KB = 64;       // k per pipeline block: 8 packed words per row, one 128-byte swizzle row of fp16 activations
+constexpr int WST = 8;       // packed-weight smem stages (4 KB each)
+constexpr int AST = 4;       // TMEM A stages (32 columns each)
+constexpr int BST = 4;       // activation smem stages
+constexpr int W_STAGE_BYTES = 8 * TMN * 4;
+constexpr int THREADS = 14 * 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// K-major SWIZZLE_128B smem descriptor (rows 128 B apart, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t mask, uint32_t magic) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(magic));  // (a & mask) | magic
+  return d;
+}
+__device__ __forceinline__ uint32_t h2_sub_mul(uint32_t v, uint32_t zc, uint32_t s2) {
+  __half2 h = __hsub2(*reinterpret_cast<__half2*>(&v), *reinterpret_cast<__half2*>(&zc));   // exact: small integers
+  h = __hmul2(h, *reinterpret_cast<__half2*>(&s2));                                         // the one rounding of recover()
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+struct Params {
+  const void* x;
+  int x_dtype;
+  int M, K, N;
+  int NT;              // batch tile = MMA N (multiple of 16, >= M)
+  int g, G;
+  int kb_per_split;    // 64-k blocks per split
+  const int32_t* qzeros;
+  const __half* scales;
+  const void* bias;
+  int bias_dtype;
+  const float* input_scale;
+  void* y;
+  int y_dtype;
+  float* part_ws;      // [tiles][splits][NT][128] fp32 partial tiles (split-K only)
+  int* counters;       // [tiles], zero on entry and on exit
+  int pdl;
+};
+
+__device__ __forceinline__ float load_as_float(const void* p, int dtype, int64_t i) {
+  if (dtype == B200WOQ_F32) return ((const float*)p)[i];
+  if (dtype == B200WOQ_F16) return __half2float(((const __half*)p)[i]);
+  return __bfloat162float(((const __nv_bfloat16*)p)[i]);
+}
+__device__ __forceinline__ void store_from_float(void* p, int dtype, int64_t i, float v) {
+  if (dtype == B200WOQ_F32)
+    ((float*)p)[i] = v;
+  else if (dtype == B200WOQ_F16)
+    ((__half*)p)[i] = __float2half_rn(v);
+  else
+    ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+}
+
+// grid (N / 128, splits); block 448
+__global__ void __launch_bounds__(THREADS, 1)
+    woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const Params p, uint32_t idesc) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const int NT = p.NT;
+  const uint32_t b_stage_bytes = (uint32_t)NT * 128;
+  const uint32_t w_ring = base;                                   // WST x 4 KB
+  const uint32_t b_ring = base + WST * W_STAGE_BYTES;             // BST x NT x 128 B (1024-aligned: NT % 16 == 0 -> multiple of 2 KB)
+  const uint32_t bars = b_ring + BST * (uint32_t)(128 * 128);      // sized for NT = 128
+  auto full_w = [&](int s) { return bars + 8u * s; };
+  auto empty_w = [&](int s) { return bars + 8u * (WST + s); };
+  auto a_full = [&](int s) { return bars + 8u * (2 * WST + s); };
+  auto a_empty = [&](int s) { return bars + 8u * (2 * WST + AST + s); };
+  auto b_full = [&](int s) { return bars + 8u * (2 * WST + 2 * AST + s); };
+  auto b_empty = [&](int s) { return bars + 8u * (2 * WST + 2 * AST + BST + s); };
+  const uint32_t d_full = bars + 8u * (2 * WST + 2 * AST + 2 * BST);
+  const uint32_t tmem_slot = d_full + 8;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  int* flag_ptr = reinterpret_cast<int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * TMN;
+  const int nkb_total = p.K / KB;
+  const int kb0 = blockIdx.y * p.kb_per_split;
+  const int nkb = min(p.kb_per_split, nkb_total - kb0);
+  const uint32_t d_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : 128;
+  const uint32_t tmem_cols = d_cols + AST * 32 <= 256 ? 256 : 512;   // power of two >= D + A stages
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WST; ++s) {
+      mbar_init(full_w(s), 1);
+      mbar_init(empty_w(s), 128);
+    }
+    for (int s = 0; s < AST; ++s) {
+      mbar_init(a_full(s), 128);
+      mbar_init(a_empty(s), 1);
+    }
+    for (int s = 0; s < BST; ++s) {
+      mbar_init(b_full(s), 128);
+      mbar_init(b_empty(s), 1);
+    }
+    mbar_init(d_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_a0 = tmem_base + d_cols;   // A stages behind the accumulator columns
+
+  if (warp == 0) {
+    // ---------------- TMA producer: packed weights are constants, they may stream before the dependency resolves
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % WST;
+        mbar_wait(empty_w(s), (((uint32_t)(i / WST)) & 1u) ^ 1u);
+        mbar_expect_tx(full_w(s), W_STAGE_BYTES);
+        tma_load_2d(w_ring + s * W_STAGE_BYTES, &map_w, full_w(s), n0, (kb0 + i) * 8);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int ta = i % AST, tb = i % BST;
+        mbar_wait(a_full(ta), ((uint32_t)(i / AST)) & 1u);
+        mbar_wait(b_full(tb), ((uint32_t)(i / BST)) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sb = b_ring + tb * b_stage_bytes;
+#pragma unroll
+        for (int k4 = 0; k4 < KB / 16; ++k4)
+          umma_f16_ts(tmem_base, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8), make_desc_k(sb + k4 * 32), idesc, (i | k4) ? 1u : 0u);
+        umma_commit(a_empty(ta));
+        umma_commit(b_empty(tb));
+      }
+      umma_commit(d_full);
+    }
+  } else if (warp < 10) {
+    // ---------------- dequant: group dg handles blocks i = dg, dg + 2, ...; thread = out-channel row
+    const int dg = (warp - 2) >> 2;
+    const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    const int nl = q * 32 + lane;              // row inside the tile
+    const int n = n0 + nl;
+    const int Nw = p.N >> 3;
+    auto fetch_sz = [&](int i, uint32_t& s2, uint32_t& zlo, uint32_t& zhi) {
+      const int gi = ((kb0 + i) * KB) / p.g;
+      const __half s = p.scales[(int64_t)gi * p.N + n];
+      const uint32_t zw = (uint32_t)p.qzeros[(int64_t)gi * Nw + (n >> 3)];
+      const uint32_t z = (((zw >> (4 * (n & 7))) & 0xfu) + 1u) & 0xfu;   // stored minus one (modules.py:363, 409-410)
+      const __half2 sh = __half2half2(s);
+      s2 = *reinterpret_cast<const uint32_t*>(&sh);
+      const __half2 zl = __half2half2(__ushort_as_half((unsigned short)(0x6400u + z)));   // 1024 + z
+      const __half2 zh = __floats2half2_rn(64.f + (float)z, 64.f + (float)z);             // 64 + z
+      zlo = *reinterpret_cast<const uint32_t*>(&zl);
+      zhi = *reinterpret_cast<const uint32_t*>(&zh);
+    };
+    uint32_t s2 = 0, zlo = 0, zhi = 0, s2n = 0, zlon = 0, zhin = 0;
+    if (dg < nkb) fetch_sz(dg, s2, zlo, zhi);
+    for (int i = dg; i < nkb; i += 2) {
+      if (i + 2 < nkb) fetch_sz(i + 2, s2n, zlon, zhin);   // prefetch the next block's scale / zero-point
+      const int s = i % WST, ta = i % AST;
+      mbar_wait(full_w(s), ((uint32_t)(i / WST)) & 1u);
+      const uint32_t* wsm = reinterpret_cast<const uint32_t*>(base_ptr + s * W_STAGE_BYTES) + nl;
+      uint32_t wd[8];
+#pragma unroll
+      for (int kw = 0; kw < 8; ++kw) wd[kw] = wsm[kw * TMN];
+      mbar_arrive(empty_w(s));                 // words are in registers
+      uint32_t a[32];
+#pragma unroll
+      for (int kw = 0; kw < 8; ++kw) {
+        const uint32_t w = wd[kw], w8 = w >> 8;
+        a[4 * kw + 0] = h2_sub_mul(lop3_and_or(w, 0x000f000fu, 0x64006400u), zlo, s2);    // (k0, k4)
+        a[4 * kw + 1] = h2_sub_mul(lop3_and_or(w, 0x00f000f0u, 0x54005400u), zhi, s2);    // (k1, k5)
+        a[4 * kw + 2] = h2_sub_mul(lop3_and_or(w8, 0x000f000fu, 0x64006400u), zlo, s2);   // (k2, k6)
+        a[4 * kw + 3] = h2_sub_mul(lop3_and_or(w8, 0x00f000f0u, 0x54005400u), zhi, s2);   // (k3, k7)
+      }
+      mbar_wait(a_empty(ta), (((uint32_t)(i / AST)) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      tmem_st32(tmem_a0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ta * 32), a);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(a_full(ta));
+      s2 = s2n;
+      zlo = zlon;
+      zhi = zhin;
+    }
+  } else {
+    // ---------------- activation staging (B operand), then the epilogue
+    const int st = threadIdx.x - 10 * 32;      // 0..127
+    const int q = warp & 3;
+    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int chunks = NT * 8;                 // 16-byte chunks per stage
+    for (int i = 0; i < nkb; ++i) {
+      const int tb = i % BST;
+      mbar_wait(b_empty(tb), (((uint32_t)(i / BST)) & 1u) ^ 1u);
+      uint8_t* sb = base_ptr + (b_ring - base) + tb * b_stage_bytes;
+      const int64_t kbase = (int64_t)(kb0 + i) * KB;
+      for (int c = st; c < chunks; c += 128) {
+        const int m = c >> 3, ch = c & 7;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (m < p.M) {
+          float v[8];
+          const int64_t idx = (int64_t)m * p.K + kbase + ch * 8;
+          if (p.x_dtype == B200WOQ_F32) {
+            const float4 f0 = *reinterpret_cast<const float4*>((const float*)p.x + idx);
+            const float4 f1 = *reinterpret_cast<const float4*>((const float*)p.x + idx + 4);
+            v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
+          } else {
+            const uint4 r = *reinterpret_cast<const uint4*>((const uint16_t*)p.x + idx);
+            const uint32_t h[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.x_dtype == B200WOQ_F16) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
+                v[2 * e] = f.x;
+                v[2 * e + 1] = f.y;
+              } else {
+                v[2 * e] = __uint_as_float(h[e] << 16);
+                v[2 * e + 1] = __uint_as_float(h[e] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.input_scale) {
+            const float4 s0 = *reinterpret_cast<const float4*>(p.input_scale + kbase + ch * 8);
+            const float4 s1 = *reinterpret_cast<const float4*>(p.input_scale + kbase + ch * 8 + 4);
+            v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+          }
+          // k order inside the 8-chunk = the order the nibble extraction produces: [0,4,1,5,2,6,3,7]
+          const __half2 h0 = __floats2half2_rn(v[0], v[4]), h1 = __floats2half2_rn(v[1], v[5]);
+          const __half2 h2 = __floats2half2_rn(v[2], v[6]), h3 = __floats2half2_rn(v[3], v[7]);
+          o.x = *reinterpret_cast<const uint32_t*>(&h0);
+          o.y = *reinterpret_cast<const uint32_t*>(&h1);
+          o.z = *reinterpret_cast<const uint32_t*>(&h2);
+          o.w = *reinterpret_cast<const uint32_t*>(&h3);
+        }
+        *reinterpret_cast<uint4*>(sb + m * 128 + ((ch ^ (m & 7)) << 4)) = o;   // SWIZZLE_128B: chunk index XOR row % 8
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+      mbar_arrive(b_full(tb));
+    }
+    // ---- epilogue: lane quarter q, thread = out-channel n0 + 32 q + lane
+    mbar_wait(d_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int nl = q * 32 + lane, n = n0 + nl;
+    const int splits = gridDim.y;
+    const float bias = (p.bias && n < p.N) ? load_as_float(p.bias, p.bias_dtype, n) : 0.f;
+    if (splits == 1) {
+      for (int c = 0; c < NT; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+#pragma unroll
+        for (int v = 0; v < 16; ++v)
+          if (c + v < p.M) store_from_float(p.y, p.y_dtype, (int64_t)(c + v) * p.N + n, __uint_as_float(r[v]) + bias);
+      }
+    } else {
+      float* mine = p.part_ws + ((size_t)(blockIdx.x * splits + blockIdx.y) * NT) * TMN + nl;
+      for (int c = 0; c < NT; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+#pragma unroll
+        for (int v = 0; v < 16; ++v)
+          if (c + v < p.M) mine[(size_t)(c + v) * TMN] = __uint_as_float(r[v]);
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (st == 0) *flag_ptr = atomicAdd(p.counters + blockIdx.x, 1);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (*flag_ptr == splits - 1) {   // last CTA of this tile: fixed-order sum over the splits
+        __threadfence();
+        const float* t0 = p.part_ws + ((size_t)(blockIdx.x * splits) * NT) * TMN + nl;
+        for (int m = 0; m < p.M; ++m) {
+          float acc = 0.f;
+          for (int s = 0; s < splits; ++s) acc += __ldcg(t0 + ((size_t)s * NT + m) * TMN);
+          store_from_float(p.y, p.y_dtype, (int64_t)m * p.N + n, acc + bias);
+        }
+        if (st == 0) p.counters[blockIdx.x] = 0;
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+}  // namespace woqtc
+
+// shape gate for the tensor-core path
+bool woq_tc_shape_ok(int64_t M, int64_t N, int64_t K, int bits, int g, const int32_t* g_idx) {
+  return bits == 4 && !g_idx && M >= 1 && M <= 128 && (N % 128) == 0 && (K % 64) == 0 && g > 0 && (g % 64) == 0 && (K % g) == 0;
+}
+
+static void woq_tc_plan(int64_t M, int64_t N, int64_t K, int* NT, int* splits, int* per) {
+  *NT = (int)(ceil_div(M, 16) * 16);
+  const int64_t tiles = N / 128;
+  const int nkb = (int)(K / 64);
+  const int sms = num_sms();
+  int s = 1;
+  if (tiles < sms) {
+    s = (int)std::max<int64_t>(1, sms / tiles);
+    s = std::min(s, std::max(1, nkb / 8));
+    s = std::min(s, 16);
+  }
+  int p = (int)ceil_div(nkb, s);
+  s = (int)ceil_div(nkb, p);
+  *splits = s;
+  *per = p;
+}
+
+int64_t woq_tc_workspace_bytes(int64_t M, int64_t N, int64_t K) {
+  int NT, s, per;
+  woq_tc_plan(M, N, K, &NT, &s, &per);
+  const int64_t tiles = N / 128;
+  return 256 + tiles * 4 + (s > 1 ? tiles * s * NT * 128 * 4 : 0) + 256;
+}
+
+// workspace: [counters: tiles ints (zero on entry, left zero)][pad to 256][partials]
+int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, const int32_t* qweight, const int32_t* qzeros,
+                   const __half* scales, const void* bias, int bias_dtype, const float* input_scale, void* y, int y_dtype,
+                   int g, void* workspace, int64_t workspace_bytes, int pdl, cudaStream_t st) {
+  using namespace woqtc;
+  if (workspace_bytes < woq_tc_workspace_bytes(M, N, K) || !workspace) {
+    set_error("woq_tc_forward: workspace too small");
+    return B200WOQ_EWORKSPACE;
+  }
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return B200WOQ_EUNSUPPORTED;
+  CUtensorMap map_w;
+  const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)(K / 8)};
+  const cuuint64_t strides[1] = {(cuuint64_t)N * 4};
+  const cuuint32_t box[2] = {128, 8};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t*>(qweight), dims, strides, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    set_error("woq_tc_forward: cuTensorMapEncodeTiled failed");
+    return B200WOQ_ECUDA;
+  }
+  Params p = {};
+  p.x = x; p.x_dtype = x_dtype; p.M = (int)M; p.K = (int)K; p.N = (int)N; p.g = g; p.G = (int)(K / g);
+  p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.bias_dtype = bias_dtype; p.input_scale = input_scale;
+  p.y = y; p.y_dtype = y_dtype; p.pdl = pdl;
+  int splits;
+  woq_tc_plan(M, N, K, &p.NT, &splits, &p.kb_per_split);
+  p.counters = (int*)workspace;
+  const int64_t tiles = N / 128;
+  p.part_ws = (float*)((uint8_t*)workspace + ((tiles * 4 + 255) / 256) * 256);
+  // instruction descriptor: D = F32 (1), A = B = F16 (0), both K-major, N = NT, M = 128
+  const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const size_t smem = (size_t)WST * W_STAGE_BYTES + (size_t)BST * 128 * 128 + 512 + 1024;
+  WOQ_CUDA(cudaFuncSetAttribute(woq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles, (unsigned)splits);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  WOQ_CUDA(cudaLaunchKernelEx(&cfg, woq_gemm_tc_kernel, map_w, p, idesc));
+  count_launch(1);
+  return 0;
+}
+
+}  // namespace b200woq

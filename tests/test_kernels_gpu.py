@@ -421,3 +421,37 @@ def test_gptq_rebuild_q_matches_column_loop(ops, golden_gptq):
                                  v["group_size"], v["bits"], v["sym"], v["mse"])
         Q2 = ops.gptq_rebuild_q(r["codes"], r["scale"], r["zero"], v["group_size"])
         assert torch.equal(Q2, r["Q"]), v
+
+
+# ------------------------------------------------------------------ K6 on tcgen05: batches of 9..128 rows
+@pytest.mark.parametrize("sym", [True, False])
+@pytest.mark.parametrize("N,K,g", [(256, 512, 64), (4096, 4096, 128), (11008, 4096, 128), (4096, 11008, 128), (384, 1024, 256)])
+def test_woq_linear_tcgen05_batches(ops, sym, N, K, g, parity_log):
+    """woq_tc.cu: out-channels as MMA-M, dequantised A tile written straight to tensor memory.  The dequantised weight is
+    the reference's fp16 recover() bit for bit (exact q - zp, one rounding in the scale multiply), so against an fp32
+    matmul with that weight only the accumulation order differs."""
+    gen = torch.Generator().manual_seed(N + K + g + 7)
+    W = torch.randn(N, K, generator=gen) * 0.02
+    q, s, z = O.rtn_quantize(W, 4, g, "sym" if sym else "asym")
+    qw, qz, sc = O.pack_optimum(q, s, z, 4, g)
+    bias = (torch.randn(N, generator=gen) * 0.1).half()
+    w_ref = O.recover_fp16(qw, qz, sc, 4, g, K, N).float()
+    dq, dz, ds, db = qw.to(DEV), qz.to(DEV), sc.to(DEV), bias.to(DEV)
+    worst = 0.0
+    for M in (9, 16, 17, 33, 64, 100, 128):
+        x = torch.randn(M, K, generator=gen).half()
+        ref = torch.nn.functional.linear(x.float(), w_ref, bias.float())
+        y = ops.woq_linear(x.to(DEV), dq, dz, ds, db, 4, g, K, N, out_dtype=torch.float32)
+        rel = _rel(y.cpu(), ref)
+        worst = max(worst, rel)
+        assert rel < 2e-4, (sym, N, K, g, M, rel)
+        y2 = ops.woq_linear(x.to(DEV), dq, dz, ds, db, 4, g, K, N, out_dtype=torch.float32)
+        assert torch.equal(y, y2)                                   # deterministic split-K
+        yh = ops.woq_linear(x.to(DEV), dq, dz, ds, db, 4, g, K, N, out_dtype=torch.float16, flags=2)
+        assert _rel(yh.float().cpu(), ref) < 2e-3
+    isc = torch.rand(K, generator=gen) + 0.5
+    x = torch.randn(24, K, generator=gen).half()
+    ref = torch.nn.functional.linear((x.float() * isc).half().float(), w_ref, bias.float())
+    y = ops.woq_linear(x.to(DEV), dq, dz, ds, db, 4, g, K, N, input_scale=isc.to(DEV), out_dtype=torch.float32)
+    assert _rel(y.cpu(), ref) < 2e-4
+    parity_log(f"woq_tc/{N}x{K}g{g}{'s' if sym else 'a'}", dict(worst_rel_vs_fp32_matmul_of_recovered_weight=worst))

@@ -54,7 +54,7 @@ def bench_gemv(out, stream_only=False):
         copies = min(64, max(4, int(math.ceil(400e6 / (N * K / 2)))))  # rotate over > L2-size worth of weights
         packs = [make_packed(N, K, seed=i) for i in range(copies)]
         layouts = [ops.build_stream_layout(qw, qz, sc, 4, 128, K, N) for (qw, qz, sc) in packs]
-        for M in (1, 2, 4):
+        for M in [int(v) for v in os.environ.get("B200WOQ_BENCH_MS", "1,2,4").split(",")]:
             x = torch.randn(M, K, device=DEV, dtype=torch.float16)
             y = torch.empty(M, N, device=DEV, dtype=torch.float16)
             for flags in ((2,) if stream_only else (0, 2)):
