@@ -23,7 +23,7 @@ from .. import ops
 
 # Batches up to this many rows take the per-warp TMA-ring kernel on the derived stream layout (woq_stream.cu); larger
 # batches amortise the weight read over more rows and use the cluster split-K kernel on the optimum tensors.
-STREAM_MAX_ROWS = int(os.environ.get("B200WOQ_STREAM_MAX_ROWS", "8"))
+STREAM_MAX_ROWS = int(os.environ.get("B200WOQ_STREAM_MAX_ROWS", "4"))
 # Above this many rows the fused dequant-GEMM kernels (tuned for the HBM-bound decode regime) hand over to
 # dequantize + cuBLAS.
 GEMM_MAX_ROWS = int(os.environ.get("B200WOQ_GEMM_MAX_ROWS", "128"))

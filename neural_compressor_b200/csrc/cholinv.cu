@@ -195,27 +195,110 @@ __global__ void __launch_bounds__(256, 2) trinv_level_kernel(float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Diagonal tile: A_kk <- inv(chol(A_kk)) in shared memory, one CTA of 256 threads.
-//   S[128][129] right-looking Cholesky (IEEE sqrt / division; two threads per row for the rank-1 updates), then the
-//   inverse X[128][129] by the same recursive doubling as the big matrix, at 32-granularity: the four 32x32 diagonal
-//   blocks by column-parallel forward substitution (one warp each), then X21 = -X22 (L21 X11) for 32- and 64-blocks.
+// Diagonal tile: A_kk <- X = inv(chol(A_kk)) in shared memory, one CTA of 256 threads (the critical path of the whole
+// factorisation: nothing else runs while it does, so it is written for latency).
+//   Recursive 2 x 2 splitting down to 32 x 32 base blocks:
+//       [A11 .  ]      L11 = chol(A11), X11 = inv(L11)                  (recursion / base)
+//       [A21 A22]      L21 = A21 X11^T ; A22 -= L21 L21^T               (shared-memory FFMA GEMMs, 4 x 4 per thread)
+//                      L22 = chol(A22), X22 = inv(L22)                  (recursion / base)
+//                      X21 = -X22 (L21 X11)
+//   Base block (one warp, registers + shuffles, fully unrolled): lane i holds row i; right-looking Cholesky with the
+//   pivot / column broadcast by __shfl, then the inverse by forward substitution with lane = column.  IEEE sqrt and
+//   division.  Only X (and the L21 blocks it needs on the way) is ever materialised: L_kk itself is not needed.
 constexpr int SP = TB + 1;
 
-// C[M x N] (ldc = SP) = alpha * A[M x K] (lda = SP) * B[K x N] (ldb = SP), all in shared memory, 256 threads
+// C[M x N] (+)= alpha * A[M x K] * op(B); all operands in shared memory with row stride SP; M, N multiples of 4.
+//   BT = false: op(B) = B[K x N];  BT = true: op(B) = B^T with B[N x K].   ACC: C += (else C =).
+template <bool BT, bool ACC>
 __device__ __forceinline__ void smem_gemm(const float* A, const float* B, float* Cm, int M, int N, int K, float alpha) {
-  for (int e = threadIdx.x; e < M * N; e += 256) {
-    const int i = e / N, j = e - i * N;
-    float sum = 0.f;
-    for (int m = 0; m < K; ++m) sum = fmaf(A[i * SP + m], B[m * SP + j], sum);
-    Cm[i * SP + j] = alpha * sum;
+  const int tiles_n = N >> 2, tiles = (M >> 2) * tiles_n;
+  for (int t = threadIdx.x; t < tiles; t += 256) {
+    const int i0 = (t / tiles_n) << 2, j0 = (t % tiles_n) << 2;
+    float acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+    for (int k = 0; k < K; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = A[(i0 + u) * SP + k];
+#pragma unroll
+      for (int v = 0; v < 4; ++v) b[v] = BT ? B[(j0 + v) * SP + k] : B[k * SP + j0 + v];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(a[u], b[v], acc[u][v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        float* c = Cm + (i0 + u) * SP + j0 + v;
+        *c = ACC ? fmaf(alpha, acc[u][v], *c) : alpha * acc[u][v];
+      }
   }
+}
+
+// 32 x 32 base block at (lo, lo): reads the lower triangle of S, writes X = inv(chol(.)) (lower, zeros above) to Xo.
+// One warp; fully unrolled so that the row / column live in registers.
+__device__ __forceinline__ void invchol32(const float* S, float* Xo, int lo, int lane, int* info, int col_base) {
+  float a[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = S[(lo + lane) * SP + lo + c];
+  bool bad = false;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float piv = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(piv > 0.f)) bad = true;
+    const float d = __fsqrt_rn(piv);
+    const float l = (lane == j) ? d : __fdiv_rn(a[j], d);      // L[lane][j] (rows above the diagonal: unused garbage)
+    a[j] = l;
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) {
+      const float lc = __shfl_sync(0xffffffffu, l, c);         // L[c][j]
+      a[c] = fmaf(-l, lc, a[c]);
+    }
+    if (bad && lane == 0 && j == 31) atomicCAS(info, 0, col_base + lo + 1);
+  }
+  // inverse, lane = column: x[r] = X[r][lane]
+  float x[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    float sum = 0.f;
+#pragma unroll
+    for (int m = 0; m < r; ++m) sum = fmaf(__shfl_sync(0xffffffffu, a[m], r), (m >= lane) ? x[m] : 0.f, sum);
+    const float lrr = __shfl_sync(0xffffffffu, a[r], r);
+    x[r] = (r == lane) ? __fdiv_rn(1.f, lrr) : ((r > lane) ? __fdiv_rn(-sum, lrr) : 0.f);
+  }
+#pragma unroll
+  for (int r = 0; r < 32; ++r) Xo[(lo + r) * SP + lo + lane] = x[r];
+}
+
+// X = inv(chol(S[lo:lo+n, lo:lo+n])) for n = 64: two base blocks + the 32-wide off-diagonal work
+__device__ __forceinline__ void invchol64(float* S, float* X, float* Tm, int lo, int* info, int col_base) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mid = lo + 32;
+  if (warp == 0) invchol32(S, X, lo, lane, info, col_base);
+  __syncthreads();
+  smem_gemm<true, false>(S + mid * SP + lo, X + lo * SP + lo, Tm, 32, 32, 32, 1.f);       // L21 = A21 X11^T
+  __syncthreads();
+  smem_gemm<true, true>(Tm, Tm, S + mid * SP + mid, 32, 32, 32, -1.f);                    // A22 -= L21 L21^T
+  __syncthreads();
+  if (warp == 0) invchol32(S, X, mid, lane, info, col_base);
+  // T2 = L21 X11 (while warp 0 factors A22: warps 1..7 could run it, kept simple: everyone after the barrier)
+  __syncthreads();
+  smem_gemm<false, false>(Tm, X + lo * SP + lo, Tm + 32 * SP, 32, 32, 32, 1.f);           // T2 = L21 X11
+  __syncthreads();
+  smem_gemm<false, false>(X + mid * SP + mid, Tm + 32 * SP, X + mid * SP + lo, 32, 32, 32, -1.f);   // X21 = -X22 T2
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256, 1) potrf_inv_tile_kernel(float* __restrict__ A, int64_t Cp, int k, int* __restrict__ info) {
   extern __shared__ float smem[];
-  float* S = smem;                 // [128][129] the tile, becomes L (lower)
+  float* S = smem;                 // [128][129] the tile (lower triangle is maintained)
   float* X = smem + TB * SP;       // [128][129] the inverse
-  float* Tm = smem + 2 * TB * SP;  // [64][129] scratch of the recursive inverse
+  float* Tm = smem + 2 * TB * SP;  // [128][129] scratch: L21 (64 rows) and L21 X11 (64 rows)
   float* tile = A + (int64_t)k * TB * Cp + (int64_t)k * TB;
   const int tid = threadIdx.x;
   for (int e = tid; e < TB * TB / 4; e += 256) {
@@ -228,49 +311,19 @@ __global__ void __launch_bounds__(256, 1) potrf_inv_tile_kernel(float* __restric
   }
   for (int e = tid; e < TB * SP; e += 256) X[e] = 0.f;
   __syncthreads();
-  const int row = tid >> 1, half = tid & 1;   // two threads per row
-  for (int j = 0; j < TB; ++j) {
-    const float piv = S[j * SP + j];
-    const float djj = __fsqrt_rn(piv);
-    float lij = 0.f;
-    if (row > j) lij = __fdiv_rn(S[row * SP + j], djj);
-    __syncthreads();                            // everyone has read the raw pivot / column
-    if (tid == 0) {
-      if (!(piv > 0.f)) atomicCAS(info, 0, k * TB + j + 1);   // first failing column wins (the reference raises here)
-      S[j * SP + j] = djj;
-    }
-    if (row > j && half == 0) S[row * SP + j] = lij;
-    __syncthreads();                            // column j of L is final
-    if (row > j) {
-      // columns j+1 .. row of this row, split between the two threads of the row
-      const int n = row - j, mid = j + 1 + (n >> 1);
-      const int c0 = half ? mid : j + 1, c1 = half ? row + 1 : mid;
-      for (int c = c0; c < c1; ++c) S[row * SP + c] = fmaf(-lij, S[c * SP + j], S[row * SP + c]);
-    }
-    // (the next iteration's first barrier orders these updates before anyone overwrites column j+1)
-    __syncthreads();
-  }
-  // ---- inverse of the four 32x32 diagonal blocks: warp w < 4, lane = column
-  if (tid < TB) {
-    const int b0 = (tid >> 5) * 32, c = tid;
-    X[c * SP + c] = __fdiv_rn(1.f, S[c * SP + c]);
-    for (int r = c + 1; r < b0 + 32; ++r) {
-      float sum = 0.f;
-      for (int m = c; m < r; ++m) sum = fmaf(S[r * SP + m], X[m * SP + c], sum);
-      X[r * SP + c] = __fdiv_rn(-sum, S[r * SP + r]);
-    }
-  }
+  const int col_base = k * TB;
+  invchol64(S, X, Tm, 0, info, col_base);                                                  // X11 (64 x 64)
+  smem_gemm<true, false>(S + 64 * SP, X, Tm, 64, 64, 64, 1.f);                             // L21 = A21 X11^T
   __syncthreads();
-  // ---- recursive doubling: blocks of 32 (two nodes), then 64 (one node)
-  for (int bs = 32; bs < TB; bs *= 2) {
-    for (int lo = 0; lo < TB; lo += 2 * bs) {
-      const int mid = lo + bs;
-      smem_gemm(S + mid * SP + lo, X + lo * SP + lo, Tm, bs, bs, bs, 1.f);            // T = L21 X11
-      __syncthreads();
-      smem_gemm(X + mid * SP + mid, Tm, X + mid * SP + lo, bs, bs, bs, -1.f);          // X21 = -X22 T
-      __syncthreads();
-    }
-  }
+  smem_gemm<true, true>(Tm, Tm, S + 64 * SP + 64, 64, 64, 64, -1.f);                       // A22 -= L21 L21^T
+  __syncthreads();
+  // Tm rows 0..63 hold L21 and must survive the second half: invchol64 uses scratch rows 64..127
+  invchol64(S, X, Tm + 64 * SP, 64, info, col_base);                                       // X22
+  float* T2 = S;                                                                           // A11 area is dead now: reuse it
+  smem_gemm<false, false>(Tm, X, T2, 64, 64, 64, 1.f);                                     // T2 = L21 X11
+  __syncthreads();
+  smem_gemm<false, false>(X + 64 * SP + 64, T2, X + 64 * SP, 64, 64, 64, -1.f);            // X21 = -X22 T2
+  __syncthreads();
   for (int e = tid; e < TB * TB / 4; e += 256) {
     const int r = e >> 5, c4 = (e & 31) * 4;
     *reinterpret_cast<float4*>(tile + (int64_t)r * Cp + c4) =
@@ -305,7 +358,7 @@ extern "C" int b200woq_cholinv_upper(const float* H, int64_t C, float* U, void* 
   WOQ_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
   flip_pad_kernel<<<blocks, 256, 0, st>>>(H, C, A, Cp);
   WOQ_LAUNCH_CHECK();
-  const size_t tile_smem = (2 * (size_t)TB + 64) * SP * sizeof(float);
+  const size_t tile_smem = 3 * (size_t)TB * SP * sizeof(float);
   WOQ_CUDA(cudaFuncSetAttribute(potrf_inv_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem));
   for (int k = 0; k < nt; ++k) {
     potrf_inv_tile_kernel<<<1, 256, tile_smem, st>>>(A, Cp, k, info);

@@ -589,7 +589,7 @@ int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, 
 }  // namespace b200woq
 
 static int tc_min_rows() {
-  static const int v = getenv("B200WOQ_TC_MIN_ROWS") ? atoi(getenv("B200WOQ_TC_MIN_ROWS")) : 9;
+  static const int v = getenv("B200WOQ_TC_MIN_ROWS") ? atoi(getenv("B200WOQ_TC_MIN_ROWS")) : 5;
   return v;
 }
 

@@ -331,7 +331,9 @@ __global__ void __launch_bounds__(1024) woq_gemm_stream_kernel(const Params p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Persistent variant (default): one CTA per SM, each owning a contiguous range of WHOLE strips (no cross-CTA
+// Persistent variant (B200WOQ_STREAM_IMPL=1; measured SLOWER than the strip-per-CTA kernel above on the Llama-2-7B
+// layers -- 5.5 vs 3.6 us at 4096x4096, equal at 22016x4096 -- because a decode layer is dominated by fixed per-launch
+// latency, not by balance; kept for the record and for M <= 8): one CTA per SM, each owning a contiguous range of WHOLE strips (no cross-CTA
 // reduction, deterministic); the CTA's records (strip-major = one contiguous byte range) are cut into W equal
 // contiguous pieces, one per warp, regardless of strip boundaries, so every warp streams the same number of bytes
 // whatever G is (the strip-per-CTA kernel leaves warps idle when G % warps != 0 and whole SMs idle when
@@ -668,7 +670,7 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
   p.y_dtype = y_dtype;
   p.pdl = (flags & 2) ? 1 : 0;
   // ---- persistent kernel (default): see woq_gemm_persist_kernel
-  static const int impl = getenv("B200WOQ_STREAM_IMPL") ? atoi(getenv("B200WOQ_STREAM_IMPL")) : 1;
+  static const int impl = getenv("B200WOQ_STREAM_IMPL") ? atoi(getenv("B200WOQ_STREAM_IMPL")) : 0;
   if (impl == 1) {
     PParams q = {};
     q.x = x; q.x_dtype = x_dtype; q.M = (int)M; q.K = (int)K; q.N = (int)N;

@@ -526,7 +526,7 @@ def sq_qdq_act_per_tensor(x, min_x=None, max_x=None, bits=8):
     return scale * (q - bias), q, scale, bias
 
 
-def sq_w8a8_linear(x, W, smooth, act_min, act_max, bias=None):
+def sq_w8a8_linear(x, W, smooth, act_min, act_max, bias=None, qparams=None):
     """`SQLinearWrapper` + the W8A8 QDQ simulation the reference falls back to without IPEX
     (smooth_quant/utility.py:2559-2662 wrapper, :2607-2631 static activation qparams, :652-690 / :726-755 QDQ,
     `WrapperLayer.q_dq_forward` :2707-2729), in fp32 torch-CPU ops:
@@ -534,6 +534,9 @@ def sq_w8a8_linear(x, W, smooth, act_min, act_max, bias=None):
         W' = W * smooth ; x' = x * (1 / smooth)
         q_w, s_w = per-out-channel sym int8 of W' ; q_x = clamp(round(x' / s_x + zp_x), 0, 255) with the STATIC
         (calibrated) per-tensor range of x' ; y = (s_x * (q_x - zp_x)) @ (q_w * s_w)^T + bias
+
+    `qparams` = (input_scale, s_x, zp_x) overrides the locally derived activation parameters (a device reciprocal may
+    differ from the host's in the last bit; the GEMM check wants identical codes on both sides).
 
     Returns dict(y, q_w int, s_w [N,1], q_x, s_x, zp_x).  PARITY UNPINNED (IPEX absent)."""
     x, W, smooth = _cpu(x).float(), _cpu(W).float(), _cpu(smooth).float()
@@ -545,6 +548,9 @@ def sq_w8a8_linear(x, W, smooth, act_min, act_max, bias=None):
     mx = torch.clamp((_cpu(act_max).float() * input_scale).max(), min=0.0)
     s_x = torch.clip((mx - mn) / 255.0, min=eps)
     zp_x = torch.clamp(torch.round((0 - mn) / s_x), 0, 255)
+    if qparams is not None:
+        input_scale, s_x, zp_x = (_cpu(t).float() for t in qparams)
+        s_x, zp_x = s_x.reshape(()), zp_x.reshape(())
     xs = x * input_scale
     q_x = torch.round(xs / s_x + zp_x).clamp_(0, 255)
     y = torch.nn.functional.linear(s_x * (q_x - zp_x), q_w * s_w, None if bias is None else _cpu(bias).float())

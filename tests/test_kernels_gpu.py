@@ -438,7 +438,7 @@ def test_woq_linear_tcgen05_batches(ops, sym, N, K, g, parity_log):
     w_ref = O.recover_fp16(qw, qz, sc, 4, g, K, N).float()
     dq, dz, ds, db = qw.to(DEV), qz.to(DEV), sc.to(DEV), bias.to(DEV)
     worst = 0.0
-    for M in (9, 16, 17, 33, 64, 100, 128):
+    for M in (5, 8, 9, 16, 17, 33, 64, 100, 128):
         x = torch.randn(M, K, generator=gen).half()
         ref = torch.nn.functional.linear(x.float(), w_ref, bias.float())
         y = ops.woq_linear(x.to(DEV), dq, dz, ds, db, 4, g, K, N, out_dtype=torch.float32)

@@ -57,8 +57,10 @@ def test_w8a8_linear_vs_qdq_simulation(N, K, M, parity_log):
     mod = SQLinear(lin, smooth.to(DEV), act_min.to(DEV), act_max.to(DEV))
     y = mod(x.to(DEV))
     assert y.dtype == torch.float16 and tuple(y.shape) == (M, N)
-    ref = O.sq_w8a8_linear(x, W, smooth, act_min, act_max, b)
-    assert float(mod.x_scale) == float(ref["s_x"]) and float(mod.x_zp) == float(ref["zp_x"])
+    own = O.sq_w8a8_linear(x, W, smooth, act_min, act_max, b)
+    # activation qparams: equal to the host's up to the last bit of a device reciprocal
+    assert abs(float(mod.x_scale) - float(own["s_x"])) <= 2e-7 * float(own["s_x"]) and float(mod.x_zp) == float(own["zp_x"])
+    ref = O.sq_w8a8_linear(x, W, smooth, act_min, act_max, b, qparams=(mod.input_scale, mod.x_scale, mod.x_zp))
     rel = float((y.float().cpu() - ref["y"]).norm() / ref["y"].norm())
     # exact integer arithmetic on a sample of rows / columns (fp64)
     rows = torch.arange(0, M, max(1, M // 4))[:4]
@@ -86,7 +88,7 @@ def test_w8a8_fp32_output_is_integer_exact():
         lin.bias.copy_(b)
     mod = SQLinear(lin, smooth.to(DEV), act_min.to(DEV), act_max.to(DEV))
     y = mod(x.to(DEV)).cpu()
-    ref = O.sq_w8a8_linear(x, W, smooth, act_min, act_max, b)
+    ref = O.sq_w8a8_linear(x, W, smooth, act_min, act_max, b, qparams=(mod.input_scale, mod.x_scale, mod.x_zp))
     acc = ref["q_x"].double() @ ref["q_w"].double().t()
     exact = (acc - float(ref["zp_x"]) * ref["q_w"].double().sum(1)) * float(ref["s_x"]) * ref["s_w"].double().flatten() + b.double()
     assert float((y.double() - exact).abs().max() / exact.abs().max()) < 1e-6

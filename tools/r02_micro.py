@@ -49,7 +49,7 @@ def syrk():
 
 
 def k2():
-    for C in (4096, 11008):
+    for C in [int(v) for v in os.environ.get("B200WOQ_MICRO_C", "4096,11008").split(",")]:
         g = torch.Generator().manual_seed(C)
         ch = torch.exp(torch.randn(C, generator=g) * 0.8)
         X = (torch.randn(2 * C, C, generator=g) * ch).to(DEV)
