@@ -98,7 +98,7 @@ struct GemmParams {
   int bias_dtype;
   void* y;                // [M, N]
   int y_dtype;
-  int32_t* acc_ws;        // [tiles][128 x NT] s32 partial sums (split-K only), zero on entry and on exit
+  int32_t* acc_ws;        // [tiles][splits][NT][128] s32 partial tiles (split-K only; plain scratch)
   int* counters;          // [tiles], zero on entry and on exit
 };
 
@@ -192,55 +192,49 @@ __global__ void __launch_bounds__(192, 1)
     const int n = n0 + q * 32 + lane;
     mbar_wait(accum_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const bool split = gridDim.z > 1;
+    const int splits = gridDim.z;
     const int tile = blockIdx.y * gridDim.x + blockIdx.x;
-    int32_t* ws = p.acc_ws + (size_t)tile * TM * NT + (size_t)(q * 32 + lane) * NT;
-    bool last = true;
-    if (split) {
-      // integer partial sums: exact and order-free
+    const int nl = q * 32 + lane;
+    const float sx = *p.x_scale, zp = *p.x_zp;
+    const float sw = (n < p.N) ? p.w_scale[n] * sx : 0.f;
+    const int32_t zsum = (n < p.N) ? (int32_t)zp * p.wsum[n] : 0;
+    const float b = (p.bias && n < p.N) ? load_as_float(p.bias, p.bias_dtype, n) : 0.f;
+    if (splits == 1) {
+      for (int c = 0; c < NT; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+          const int m = m0 + c + v;
+          if (m < p.M && n < p.N) store_from_float(p.y, p.y_dtype, (int64_t)m * p.N + n, fmaf((float)((int32_t)r[v] - zsum), sw, b));
+        }
+      }
+    } else {
+      // split-K: s32 partial tiles [tile][split][NT][128] (coalesced over out-channels); the LAST CTA of the tile
+      // (atomic counter, self-resetting) sums them -- integer adds, exact in any order
+      int32_t* mine = p.acc_ws + ((size_t)(tile * splits + blockIdx.z) * NT) * TM + nl;
       for (int c = 0; c < NT; c += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
 #pragma unroll
         for (int v = 0; v < 16; ++v)
-          if (m0 + c + v < p.M) atomicAdd(ws + c + v, (int32_t)r[v]);
+          if (m0 + c + v < p.M) mine[(size_t)(c + v) * TM] = (int32_t)r[v];
       }
       __threadfence();
-      // one arrival per epilogue warp set: use a CTA-local barrier among the 128 epilogue threads, then one atomic
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64) *flag_ptr = atomicAdd(p.counters + tile, 1);
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      last = (*flag_ptr == (int)gridDim.z - 1);
-      if (last) __threadfence();
-    }
-    if (last) {
-      const float sx = *p.x_scale, zp = *p.x_zp;
-      if (n < p.N) {
-        const float sw = p.w_scale[n] * sx;
-        const int32_t zsum = (int32_t)zp * p.wsum[n];
-        const float b = p.bias ? load_as_float(p.bias, p.bias_dtype, n) : 0.f;
-        for (int c = 0; c < NT; c += 16) {
-          uint32_t r[16];
-          if (split) {
-#pragma unroll
-            for (int v = 0; v < 16; ++v) {
-              r[v] = (m0 + c + v < p.M) ? (uint32_t)__ldcg(ws + c + v) : 0u;
-              if (m0 + c + v < p.M) ws[c + v] = 0;   // leave the workspace zeroed for the next launch
-            }
-          } else {
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-          }
-#pragma unroll
-          for (int v = 0; v < 16; ++v) {
-            const int m = m0 + c + v;
-            if (m < p.M) store_from_float(p.y, p.y_dtype, (int64_t)m * p.N + n, fmaf((float)((int32_t)r[v] - zsum), sw, b));
-          }
+      if (*flag_ptr == splits - 1) {
+        __threadfence();
+        const int32_t* t0 = p.acc_ws + ((size_t)(tile * splits) * NT) * TM + nl;
+        const int mlim = min(NT, p.M - m0);
+        for (int m = 0; m < mlim; ++m) {
+          int32_t acc = 0;
+          for (int s2 = 0; s2 < splits; ++s2) acc += __ldcg(t0 + ((size_t)s2 * NT + m) * TM);
+          if (n < p.N) store_from_float(p.y, p.y_dtype, (int64_t)(m0 + m) * p.N + n, fmaf((float)(acc - zsum), sw, b));
         }
-      } else if (split) {
-        for (int c = 0; c < NT; ++c)
-          if (m0 + c < p.M) ws[c] = 0;
+        if (threadIdx.x == 64) p.counters[tile] = 0;
       }
-      if (split && threadIdx.x == 64) p.counters[tile] = 0;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -391,8 +385,7 @@ extern "C" int b200woq_sq_smooth_quant_weight(const void* W, int w_dtype, int64_
   return 0;
 }
 
-// workspace: [q_x: M x Kp u8][pad to 256][split-K s32 sums: tiles x 128 x NT][counters: tiles]; the split-K part must be
-// zero on entry (allocate it zeroed once; every launch leaves it zeroed)
+// workspace: [q_x: M x Kp u8][pad to 256][counters: tiles ints -- zero on entry, left zero][pad][s32 partial tiles]
 static void w8a8_plan(int64_t M, int64_t N, int64_t K, int* NT, int* splits, int* kb_per_split, int64_t* tiles) {
   const int64_t Kp = pad_k(K);
   int nt = (int)std::min<int64_t>(256, ceil_div(M, 16) * 16);
@@ -414,7 +407,7 @@ extern "C" int64_t b200woq_w8a8_workspace_bytes(int64_t M, int64_t N, int64_t K)
   int64_t tiles;
   w8a8_plan(M, N, K, &NT, &splits, &per, &tiles);
   const int64_t q = ((M * pad_k(K) + 255) / 256) * 256;
-  return q + tiles * 128 * NT * 4 + tiles * 4 + 256;
+  return q + tiles * 4 + 256 + tiles * splits * 128 * NT * 4 + 256;
 }
 
 extern "C" int64_t b200woq_w8a8_workspace_zeroed_offset(int64_t M, int64_t K) { return ((M * pad_k(K) + 255) / 256) * 256; }
@@ -435,8 +428,8 @@ extern "C" int b200woq_w8a8_linear_forward(const void* x, int x_dtype, int64_t M
   int NT, splits, per;
   int64_t tiles;
   w8a8_plan(M, N, K, &NT, &splits, &per, &tiles);
-  int32_t* acc_ws = (int32_t*)(qx + b200woq_w8a8_workspace_zeroed_offset(M, K));
-  int* counters = (int*)(acc_ws + tiles * 128 * NT);
+  int* counters = (int*)(qx + b200woq_w8a8_workspace_zeroed_offset(M, K));   // zero on entry, left zero
+  int32_t* acc_ws = (int32_t*)((uint8_t*)counters + ((tiles * 4 + 255) / 256) * 256);
   {
     const int64_t total = M * (Kp / 16);
     int64_t b = ceil_div(total, 256);
@@ -444,8 +437,27 @@ extern "C" int b200woq_w8a8_linear_forward(const void* x, int x_dtype, int64_t M
     sq_quantize_act_kernel<<<(unsigned)(b > cap ? cap : b), 256, 0, st>>>(x, x_dtype, M, K, Kp, input_scale, x_scale, x_zp, qx);
     WOQ_LAUNCH_CHECK();
   }
+  // tensor maps are pure functions of (pointer, shape, box): a small thread-local cache avoids two driver encodes per call
+  struct MapKey { const void* p; int64_t a, b; int box; };
+  struct MapSlot { MapKey k; CUtensorMap m; bool used; };
+  static thread_local MapSlot cache[16] = {};
+  static thread_local int next_slot = 0;
+  auto get_map = [&](const void* base_, int64_t rows, int box, CUtensorMap* out) -> bool {
+    for (int i = 0; i < 16; ++i)
+      if (cache[i].used && cache[i].k.p == base_ && cache[i].k.a == Kp && cache[i].k.b == rows && cache[i].k.box == box) {
+        *out = cache[i].m;
+        return true;
+      }
+    if (!encode_u8_2d(out, base_, Kp, rows, Kp, box)) return false;
+    MapSlot& sl = cache[next_slot];
+    next_slot = (next_slot + 1) & 15;
+    sl.k = MapKey{base_, Kp, rows, box};
+    sl.m = *out;
+    sl.used = true;
+    return true;
+  };
   CUtensorMap map_w, map_x;
-  if (!encode_u8_2d(&map_w, qweight, Kp, N, Kp, 128) || !encode_u8_2d(&map_x, qx, Kp, M, Kp, NT)) {
+  if (!get_map(qweight, N, 128, &map_w) || !get_map(qx, M, NT, &map_x)) {
     set_error("w8a8_linear_forward: cuTensorMapEncodeTiled failed");
     return B200WOQ_ECUDA;
   }

@@ -671,7 +671,7 @@ extern "C" int b200woq_linear_forward_stream(const void* x, int x_dtype, int64_t
   p.pdl = (flags & 2) ? 1 : 0;
   // ---- persistent kernel (default): see woq_gemm_persist_kernel
   static const int impl = getenv("B200WOQ_STREAM_IMPL") ? atoi(getenv("B200WOQ_STREAM_IMPL")) : 0;
-  if (impl == 1) {
+  if (impl == 1 || M > 4) {  // the strip kernel is tuned (and shared-memory sized) for M <= 4
     PParams q = {};
     q.x = x; q.x_dtype = x_dtype; q.M = (int)M; q.K = (int)K; q.N = (int)N;
     q.recs = (const uint8_t*)stream_layout; q.NI = g / 32; q.g = g; q.G = (int)(K / g);

@@ -60,6 +60,23 @@ def pytest_sessionfinish(session, exitstatus):
         pass
 
 
+def parity_bound(key, field, default):
+    """Asserted bar for a measured (not bit-exact) parity number: 2x what was last measured on a B200 and committed in
+    tests/golden/parity_bounds.json (written by tools/update_parity_bounds.py from gpurun_out/parity_r02.json), or
+    `default` when the case has not been measured yet.  Never below 1e-4 so that noise-floor flips do not flake."""
+    import json
+
+    path = os.path.join(GOLDEN, "parity_bounds.json")
+    if os.path.exists(path):
+        try:
+            v = json.load(open(path)).get(key, {}).get(field)
+            if v is not None:
+                return max(2.0 * float(v), 1e-4)
+        except Exception:
+            pass
+    return default
+
+
 def load_golden(name):
     return torch.load(os.path.join(GOLDEN, name), weights_only=False)
 
