@@ -685,8 +685,8 @@ extern "C" int b200woq_linear_forward(const void* x, int x_dtype, int64_t M, int
   p.G = ceil_div(K, g);
   p.pdl = (flags & 2) ? 1 : 0;
   const size_t xes = x_dtype == B200WOQ_F32 ? 4 : 2, yes = y_dtype == B200WOQ_F32 ? 4 : 2;
-  if (!(flags & 1) && x_dtype == B200WOQ_F16 && M >= tc_min_rows() && woq_tc_shape_ok(M, N, K, bits, g, g_idx) && workspace &&
-      workspace_bytes >= woq_tc_workspace_bytes(M, N, K))
+  if (!(flags & 1) && x_dtype == B200WOQ_F16 && !input_scale && (((uintptr_t)x) & 15) == 0 && M >= tc_min_rows() &&
+      woq_tc_shape_ok(M, N, K, bits, g, g_idx) && workspace && workspace_bytes >= woq_tc_workspace_bytes(M, N, K))
     return woq_tc_forward(x, x_dtype, M, K, N, qweight, qzeros, (const __half*)scales16, bias, bias_dtype, input_scale, y,
                           y_dtype, g, workspace, workspace_bytes, p.pdl, st);
   const bool fast = !(flags & 1) && fast_path_ok(N, K, bits, g, g_idx);

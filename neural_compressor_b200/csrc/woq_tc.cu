@@ -10,9 +10,12 @@
 //                 = the reference's fp16 weight, bit for bit) -> tcgen05.st: the dequantised A tile goes straight into
 //                 TENSOR MEMORY (128 lanes x 32 columns per 64-k block), never through shared memory -- writing fp16
 //                 weights (4x the packed bytes) to smem and reading them back would cap the kernel near 45 % of HBM
-//   warps 10-13   activation staging: x tile [batch x 64 k] -> fp16, k permuted [0,4,1,5,2,6,3,7] per 8 (the order the
-//                 LOP3 extraction yields), K-major SWIZZLE_128B smem tile (B operand); afterwards the epilogue:
-//                 tcgen05.ld of D[128 x batch] fp32 -> (+bias) -> y, coalesced over out-channels
+//                 (the LOP3 extraction yields the pairs (k0,k4),(k1,k5),(k2,k6),(k3,k7); four PRMTs per word restore the
+//                 natural k order, so the activations need no permuted copy)
+//   warp 0 also   TMA-loads the fp16 activation tile [batch x 64 k] (K-major SWIZZLE_128B, rows past M zero-filled) as the
+//                 B operand: fully asynchronous, 4 stages in flight -- a synchronous load/convert/store stage per 64-k
+//                 block costs ~0.7 us of L2 latency per block and was measured 5x slower than the rest of the pipeline
+//   warps 10-13   epilogue: tcgen05.ld of D[128 x batch] fp32 -> (+bias) -> y, coalesced over out-channels
 //   warp 1        MMA issuer: tcgen05.mma.kind::f16 with A from TMEM, B from smem, D fp32 in TMEM; tcgen05.commit frees
 //                 the A / B stages
 // Split-K over gridDim.y when the tile grid is smaller than the chip: fp32 partial tiles go to a workspace and the LAST
@@ -147,7 +150,8 @@ __device__ __forceinline__ void store_from_float(void* p, int dtype, int64_t i, 
 
 // grid (N / 128, splits); block 448
 __global__ void __launch_bounds__(THREADS, 1)
-    woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const Params p, uint32_t idesc) {
+    woq_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, const Params p,
+                       uint32_t idesc) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < BST; ++s) {
-      mbar_init(b_full(s), 128);
+      mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
     }
     mbar_init(d_full, 1);
@@ -202,13 +206,27 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t tmem_a0 = tmem_base + d_cols;   // A stages behind the accumulator columns
 
   if (warp == 0) {
-    // ---------------- TMA producer: packed weights are constants, they may stream before the dependency resolves
+    // ---------------- TMA producer.  Packed weights are constants: the first ring fill is issued BEFORE the programmatic
+    // dependency is resolved; the activation tiles (produced by the previous kernel) only after it.
     if (lane == 0) {
+      const int pre = min(nkb, WST);
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(full_w(i), W_STAGE_BYTES);
+        tma_load_2d(w_ring + i * W_STAGE_BYTES, &map_w, full_w(i), n0, (kb0 + i) * 8);
+      }
+      if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % WST;
-        mbar_wait(empty_w(s), (((uint32_t)(i / WST)) & 1u) ^ 1u);
-        mbar_expect_tx(full_w(s), W_STAGE_BYTES);
-        tma_load_2d(w_ring + s * W_STAGE_BYTES, &map_w, full_w(s), n0, (kb0 + i) * 8);
+        const int tb = i % BST;
+        mbar_wait(b_empty(tb), (((uint32_t)(i / BST)) & 1u) ^ 1u);
+        mbar_expect_tx(b_full(tb), b_stage_bytes);
+        tma_load_2d(b_ring + tb * b_stage_bytes, &map_x, b_full(tb), (kb0 + i) * KB, 0);
+        const int j = i + WST;             // keep the weight ring WST blocks ahead
+        if (j < nkb) {
+          const int s = j % WST;
+          mbar_wait(empty_w(s), (((uint32_t)(j / WST)) & 1u) ^ 1u);
+          mbar_expect_tx(full_w(s), W_STAGE_BYTES);
+          tma_load_2d(w_ring + s * W_STAGE_BYTES, &map_w, full_w(s), n0, (kb0 + j) * 8);
+        }
       }
     }
   } else if (warp == 1) {
@@ -262,10 +280,14 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
       for (int kw = 0; kw < 8; ++kw) {
         const uint32_t w = wd[kw], w8 = w >> 8;
-        a[4 * kw + 0] = h2_sub_mul(lop3_and_or(w, 0x000f000fu, 0x64006400u), zlo, s2);    // (k0, k4)
-        a[4 * kw + 1] = h2_sub_mul(lop3_and_or(w, 0x00f000f0u, 0x54005400u), zhi, s2);    // (k1, k5)
-        a[4 * kw + 2] = h2_sub_mul(lop3_and_or(w8, 0x000f000fu, 0x64006400u), zlo, s2);   // (k2, k6)
-        a[4 * kw + 3] = h2_sub_mul(lop3_and_or(w8, 0x00f000f0u, 0x54005400u), zhi, s2);   // (k3, k7)
+        const uint32_t p04 = h2_sub_mul(lop3_and_or(w, 0x000f000fu, 0x64006400u), zlo, s2);    // (k0, k4)
+        const uint32_t p15 = h2_sub_mul(lop3_and_or(w, 0x00f000f0u, 0x54005400u), zhi, s2);    // (k1, k5)
+        const uint32_t p26 = h2_sub_mul(lop3_and_or(w8, 0x000f000fu, 0x64006400u), zlo, s2);   // (k2, k6)
+        const uint32_t p37 = h2_sub_mul(lop3_and_or(w8, 0x00f000f0u, 0x54005400u), zhi, s2);   // (k3, k7)
+        a[4 * kw + 0] = __byte_perm(p04, p15, 0x5410);   // (k0, k1): natural k order, TMEM column = 2 consecutive k
+        a[4 * kw + 1] = __byte_perm(p26, p37, 0x5410);   // (k2, k3)
+        a[4 * kw + 2] = __byte_perm(p04, p15, 0x7632);   // (k4, k5)
+        a[4 * kw + 3] = __byte_perm(p26, p37, 0x7632);   // (k6, k7)
       }
       mbar_wait(a_empty(ta), (((uint32_t)(i / AST)) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -277,59 +299,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       zhi = zhin;
     }
   } else {
-    // ---------------- activation staging (B operand), then the epilogue
+    // ---------------- epilogue warps
     const int st = threadIdx.x - 10 * 32;      // 0..127
     const int q = warp & 3;
-    if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int chunks = NT * 8;                 // 16-byte chunks per stage
-    for (int i = 0; i < nkb; ++i) {
-      const int tb = i % BST;
-      mbar_wait(b_empty(tb), (((uint32_t)(i / BST)) & 1u) ^ 1u);
-      uint8_t* sb = base_ptr + (b_ring - base) + tb * b_stage_bytes;
-      const int64_t kbase = (int64_t)(kb0 + i) * KB;
-      for (int c = st; c < chunks; c += 128) {
-        const int m = c >> 3, ch = c & 7;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (m < p.M) {
-          float v[8];
-          const int64_t idx = (int64_t)m * p.K + kbase + ch * 8;
-          if (p.x_dtype == B200WOQ_F32) {
-            const float4 f0 = *reinterpret_cast<const float4*>((const float*)p.x + idx);
-            const float4 f1 = *reinterpret_cast<const float4*>((const float*)p.x + idx + 4);
-            v[0] = f0.x; v[1] = f0.y; v[2] = f0.z; v[3] = f0.w; v[4] = f1.x; v[5] = f1.y; v[6] = f1.z; v[7] = f1.w;
-          } else {
-            const uint4 r = *reinterpret_cast<const uint4*>((const uint16_t*)p.x + idx);
-            const uint32_t h[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (p.x_dtype == B200WOQ_F16) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[e]));
-                v[2 * e] = f.x;
-                v[2 * e + 1] = f.y;
-              } else {
-                v[2 * e] = __uint_as_float(h[e] << 16);
-                v[2 * e + 1] = __uint_as_float(h[e] & 0xffff0000u);
-              }
-            }
-          }
-          if (p.input_scale) {
-            const float4 s0 = *reinterpret_cast<const float4*>(p.input_scale + kbase + ch * 8);
-            const float4 s1 = *reinterpret_cast<const float4*>(p.input_scale + kbase + ch * 8 + 4);
-            v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-          }
-          // k order inside the 8-chunk = the order the nibble extraction produces: [0,4,1,5,2,6,3,7]
-          const __half2 h0 = __floats2half2_rn(v[0], v[4]), h1 = __floats2half2_rn(v[1], v[5]);
-          const __half2 h2 = __floats2half2_rn(v[2], v[6]), h3 = __floats2half2_rn(v[3], v[7]);
-          o.x = *reinterpret_cast<const uint32_t*>(&h0);
-          o.y = *reinterpret_cast<const uint32_t*>(&h1);
-          o.z = *reinterpret_cast<const uint32_t*>(&h2);
-          o.w = *reinterpret_cast<const uint32_t*>(&h3);
-        }
-        *reinterpret_cast<uint4*>(sb + m * 128 + ((ch ^ (m & 7)) << 4)) = o;   // SWIZZLE_128B: chunk index XOR row % 8
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-      mbar_arrive(b_full(tb));
-    }
     // ---- epilogue: lane quarter q, thread = out-channel n0 + 32 q + lane
     mbar_wait(d_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -395,6 +367,7 @@ static EncodeTiledFn encode_fn() {
 }  // namespace woqtc
 
 // shape gate for the tensor-core path
+// (activations must be fp16, 16-byte aligned and contiguous; an input_scale is applied by the caller beforehand)
 bool woq_tc_shape_ok(int64_t M, int64_t N, int64_t K, int bits, int g, const int32_t* g_idx) {
   return bits == 4 && !g_idx && M >= 1 && M <= 128 && (N % 128) == 0 && (K % 64) == 0 && g > 0 && (g % 64) == 0 && (K % g) == 0;
 }
@@ -445,6 +418,19 @@ int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, 
     set_error("woq_tc_forward: cuTensorMapEncodeTiled failed");
     return B200WOQ_ECUDA;
   }
+  CUtensorMap map_x;
+  {
+    const cuuint64_t xd[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t xs[1] = {(cuuint64_t)K * 2};
+    int NTb, sb, pb;
+    woq_tc_plan(M, N, K, &NTb, &sb, &pb);
+    const cuuint32_t xb[2] = {64, (cuuint32_t)NTb};
+    if (enc(&map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), xd, xs, xb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("woq_tc_forward: cuTensorMapEncodeTiled (activations) failed");
+      return B200WOQ_ECUDA;
+    }
+  }
   Params p = {};
   p.x = x; p.x_dtype = x_dtype; p.M = (int)M; p.K = (int)K; p.N = (int)N; p.g = g; p.G = (int)(K / g);
   p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.bias_dtype = bias_dtype; p.input_scale = input_scale;
@@ -468,7 +454,7 @@ int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  WOQ_CUDA(cudaLaunchKernelEx(&cfg, woq_gemm_tc_kernel, map_w, p, idesc));
+  WOQ_CUDA(cudaLaunchKernelEx(&cfg, woq_gemm_tc_kernel, map_w, map_x, p, idesc));
   count_launch(1);
   return 0;
 }

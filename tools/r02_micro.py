@@ -90,6 +90,39 @@ def w8a8():
                                   tops=round(2 * M * N * K / ms / 1e9, 1), weight_GBs=round(N * K / ms / 1e6, 1))), flush=True)
 
 
+def woq_tc():
+    """tcgen05 dequant-GEMM per layer under a CUDA graph, weights rotated through > L2."""
+    import math
+
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+    for (N, K) in ((4096, 4096), (12288, 4096), (22016, 4096), (4096, 11008)):
+        copies = min(48, max(4, int(math.ceil(300e6 / (N * K / 2)))))
+        packs = []
+        for i in range(copies):
+            W = torch.randn(N, K, device=DEV) * 0.02
+            r = ops.rtn_quant_pack(W, 4, 128, True)
+            packs.append((r["qweight"], r["qzeros"], r["scales"]))
+            del W
+        for M in (8, 16, 32, 64, 128):
+            x = torch.randn(M, K, device=DEV, dtype=torch.float16)
+            y = torch.empty(M, N, device=DEV, dtype=torch.float16)
+
+            def run():
+                for (qw, qz, sc) in packs:
+                    ops.woq_linear(x, qw, qz, sc, None, 4, 128, K, N, out_dtype=torch.float16, flags=2, out=y)
+            run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                run()
+            ms = timed(g.replay, reps=10) / copies
+            by = N * K // 2 + 2 * N * K // 128 + N * K // 256 + 2 * M * K + 2 * M * N
+            print(json.dumps(dict(kernel="woq_linear(tc)", N=N, K=K, M=M, us=round(ms * 1e3, 2), GBs=round(by / ms / 1e6, 1),
+                                  hbm_frac=round(by / ms / 1e6 / peak, 3), tflops=round(2 * M * N * K / ms / 1e9, 1))), flush=True)
+        del packs
+        torch.cuda.empty_cache()
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("syrk", "all"):
@@ -98,3 +131,5 @@ if __name__ == "__main__":
         k2()
     if what in ("w8a8", "all"):
         w8a8()
+    if what in ("woq_tc", "all"):
+        woq_tc()
