@@ -33,11 +33,16 @@ namespace woqtc {
 
 constexpr int TMN = 128;     // out-channels per CTA (MMA M)
 constexpr int KB = 64;       // k per pipeline block: 8 packed words per row, one 128-byte swizzle row of fp16 activations
-constexpr int WST = 8;       // packed-weight smem stages (4 KB each)
-constexpr int AST = 4;       // TMEM A stages (32 columns each)
-constexpr int BST = 4;       // activation smem stages
+constexpr int WST = 24;      // packed-weight smem stages (4 KB each): ~2.5 us of HBM latency x the per-SM share of the
+                             // bandwidth = ~100 KB that must be in flight per SM (8 stages measured 3x too few)
+constexpr int DG = 4;        // dequant groups of 4 warps (block i belongs to group i % DG)
+constexpr int AST = 8;       // TMEM A stages (32 columns each): two per dequant group
+constexpr int BST = 32;      // max activation smem stages: as many [NT x 64 k] tiles as fit in 64 KB (32 at NT = 16, 4 at NT = 128);
+                             // the tiles are tiny, so only a deep ring keeps enough bytes in flight to cover the L2 latency
 constexpr int W_STAGE_BYTES = 8 * TMN * 4;
-constexpr int THREADS = 14 * 32;
+constexpr int DEQ_WARPS = 4 * DG;
+constexpr int EPI_WARP0 = 2 + DEQ_WARPS;   // first epilogue warp (18): 18 % 4 == 2, like warp 2, so quarters line up
+constexpr int THREADS = (EPI_WARP0 + 4) * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -132,6 +137,7 @@ struct Params {
   float* part_ws;      // [tiles][splits][NT][128] fp32 partial tiles (split-K only)
   int* counters;       // [tiles], zero on entry and on exit
   int pdl;
+  int debug;           // B200WOQ_TC_DEBUG (measurement only): 1 = issue one MMA per block instead of four, 2 = none
 };
 
 __device__ __forceinline__ float load_as_float(const void* p, int dtype, int64_t i) {
@@ -159,7 +165,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t b_stage_bytes = (uint32_t)NT * 128;
   const uint32_t w_ring = base;                                   // WST x 4 KB
   const uint32_t b_ring = base + WST * W_STAGE_BYTES;             // BST x NT x 128 B (1024-aligned: NT % 16 == 0 -> multiple of 2 KB)
-  const uint32_t bars = b_ring + BST * (uint32_t)(128 * 128);      // sized for NT = 128
+  const int bst = min(BST, (int)(65536u / b_stage_bytes));          // 64 KB of activation stages
+  const uint32_t bars = b_ring + 4 * (uint32_t)(128 * 128);
   auto full_w = [&](int s) { return bars + 8u * s; };
   auto empty_w = [&](int s) { return bars + 8u * (WST + s); };
   auto a_full = [&](int s) { return bars + 8u * (2 * WST + s); };
@@ -170,22 +177,31 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t tmem_slot = d_full + 8;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   int* flag_ptr = reinterpret_cast<int*>(smem_raw + (tmem_slot + 8 - smem_u32(smem_raw)));
+  // scales / zero-points of this CTA's 128 out-channels for ITS groups, staged once (they are constants): the dequant
+  // warps then never wait on a global load inside the pipeline
+  __half* sc_tab = reinterpret_cast<__half*>(smem_raw + (bars + 2048 - smem_u32(smem_raw)));   // [groups][128] fp16
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * TMN;
   const int nkb_total = p.K / KB;
   const int kb0 = blockIdx.y * p.kb_per_split;
   const int nkb = min(p.kb_per_split, nkb_total - kb0);
-  const uint32_t d_cols = NT <= 32 ? 32 : NT <= 64 ? 64 : 128;
-  const uint32_t tmem_cols = d_cols + AST * 32 <= 256 ? 256 : 512;   // power of two >= D + A stages
+  const int g_first = (kb0 * KB) / p.g, g_last = ((kb0 + nkb) * KB - 1) / p.g, n_groups = g_last - g_first + 1;
+  uint8_t* z_tab = reinterpret_cast<uint8_t*>(sc_tab + (size_t)n_groups * TMN);                // [groups][128] u8 (already +1)
+  // NACC independent accumulators (k-steps round-robin): successive MMAs into ONE 128 x NT tile are a dependent chain of
+  // ~60 cycles each (measured), four chains hide it; the epilogue adds them up
+  const uint32_t d_stride = NT <= 32 ? 32 : NT <= 64 ? 64 : 128;
+  const int nacc = NT <= 64 ? 4 : 2;
+  const uint32_t d_cols = d_stride * nacc;
+  const uint32_t tmem_cols = 512;   // D (<= 128 columns) + 8 A stages of 32 columns
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < WST; ++s) {
       mbar_init(full_w(s), 1);
-      mbar_init(empty_w(s), 128);
+      mbar_init(empty_w(s), 4);      // one elected arrival per dequant warp of the consuming group
     }
     for (int s = 0; s < AST; ++s) {
-      mbar_init(a_full(s), 128);
+      mbar_init(a_full(s), 4);
       mbar_init(a_empty(s), 1);
     }
     for (int s = 0; s < BST; ++s) {
@@ -199,6 +215,15 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  {
+    const int Nw = p.N >> 3;
+    for (int idx = threadIdx.x; idx < n_groups * TMN; idx += THREADS) {
+      const int gl = idx >> 7, nl = idx & 127, n = n0 + nl;
+      sc_tab[idx] = p.scales[(int64_t)(g_first + gl) * p.N + n];
+      const uint32_t zw = (uint32_t)p.qzeros[(int64_t)(g_first + gl) * Nw + (n >> 3)];
+      z_tab[idx] = (uint8_t)((((zw >> (4 * (n & 7))) & 0xfu) + 1u) & 0xfu);   // stored minus one (modules.py:363, 409-410)
+    }
+  }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -206,77 +231,70 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t tmem_a0 = tmem_base + d_cols;   // A stages behind the accumulator columns
 
   if (warp == 0) {
-    // ---------------- TMA producer.  Packed weights are constants: the first ring fill is issued BEFORE the programmatic
-    // dependency is resolved; the activation tiles (produced by the previous kernel) only after it.
+    // ---------------- TMA producer of the packed weights (constants: no dependency on the previous kernel)
     if (lane == 0) {
-      const int pre = min(nkb, WST);
-      for (int i = 0; i < pre; ++i) {
-        mbar_expect_tx(full_w(i), W_STAGE_BYTES);
-        tma_load_2d(w_ring + i * W_STAGE_BYTES, &map_w, full_w(i), n0, (kb0 + i) * 8);
-      }
-      if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int i = 0; i < nkb; ++i) {
-        const int tb = i % BST;
-        mbar_wait(b_empty(tb), (((uint32_t)(i / BST)) & 1u) ^ 1u);
-        mbar_expect_tx(b_full(tb), b_stage_bytes);
-        tma_load_2d(b_ring + tb * b_stage_bytes, &map_x, b_full(tb), (kb0 + i) * KB, 0);
-        const int j = i + WST;             // keep the weight ring WST blocks ahead
-        if (j < nkb) {
-          const int s = j % WST;
-          mbar_wait(empty_w(s), (((uint32_t)(j / WST)) & 1u) ^ 1u);
-          mbar_expect_tx(full_w(s), W_STAGE_BYTES);
-          tma_load_2d(w_ring + s * W_STAGE_BYTES, &map_w, full_w(s), n0, (kb0 + j) * 8);
-        }
+        const int s = i % WST;
+        mbar_wait(empty_w(s), (((uint32_t)(i / WST)) & 1u) ^ 1u);
+        mbar_expect_tx(full_w(s), W_STAGE_BYTES);
+        tma_load_2d(w_ring + s * W_STAGE_BYTES, &map_w, full_w(s), n0, (kb0 + i) * 8);
       }
     }
   } else if (warp == 1) {
     // ---------------- MMA issuer
     if (lane == 0) {
       for (int i = 0; i < nkb; ++i) {
-        const int ta = i % AST, tb = i % BST;
+        const int ta = i % AST, tb = i % bst;
         mbar_wait(a_full(ta), ((uint32_t)(i / AST)) & 1u);
-        mbar_wait(b_full(tb), ((uint32_t)(i / BST)) & 1u);
+        mbar_wait(b_full(tb), ((uint32_t)(i / bst)) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sb = b_ring + tb * b_stage_bytes;
 #pragma unroll
         for (int k4 = 0; k4 < KB / 16; ++k4)
-          umma_f16_ts(tmem_base, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8), make_desc_k(sb + k4 * 32), idesc, (i | k4) ? 1u : 0u);
+          umma_f16_ts(tmem_base + (uint32_t)(k4 & (nacc - 1)) * d_stride, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8),
+                      make_desc_k(sb + k4 * 32), idesc, (i > 0 || k4 >= nacc) ? 1u : 0u);
         umma_commit(a_empty(ta));
         umma_commit(b_empty(tb));
       }
       umma_commit(d_full);
     }
-  } else if (warp < 10) {
+  } else if (warp < EPI_WARP0) {
     // ---------------- dequant: group dg handles blocks i = dg, dg + 2, ...; thread = out-channel row
-    const int dg = (warp - 2) >> 2;
+    const int dg = (warp - 2) >> 2;            // 0 .. DG-1
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
     const int nl = q * 32 + lane;              // row inside the tile
     const int n = n0 + nl;
-    const int Nw = p.N >> 3;
     auto fetch_sz = [&](int i, uint32_t& s2, uint32_t& zlo, uint32_t& zhi) {
-      const int gi = ((kb0 + i) * KB) / p.g;
-      const __half s = p.scales[(int64_t)gi * p.N + n];
-      const uint32_t zw = (uint32_t)p.qzeros[(int64_t)gi * Nw + (n >> 3)];
-      const uint32_t z = (((zw >> (4 * (n & 7))) & 0xfu) + 1u) & 0xfu;   // stored minus one (modules.py:363, 409-410)
+      const int gl = ((kb0 + i) * KB) / p.g - g_first;
+      const __half s = sc_tab[gl * TMN + nl];
+      const uint32_t z = z_tab[gl * TMN + nl];
       const __half2 sh = __half2half2(s);
       s2 = *reinterpret_cast<const uint32_t*>(&sh);
       const __half2 zl = __half2half2(__ushort_as_half((unsigned short)(0x6400u + z)));   // 1024 + z
-      const __half2 zh = __floats2half2_rn(64.f + (float)z, 64.f + (float)z);             // 64 + z
+      const __half2 zh = __half2half2(__ushort_as_half((unsigned short)(0x5400u + (z << 4))));   // 64 + z
       zlo = *reinterpret_cast<const uint32_t*>(&zl);
       zhi = *reinterpret_cast<const uint32_t*>(&zh);
     };
-    uint32_t s2 = 0, zlo = 0, zhi = 0, s2n = 0, zlon = 0, zhin = 0;
-    if (dg < nkb) fetch_sz(dg, s2, zlo, zhi);
-    for (int i = dg; i < nkb; i += 2) {
-      if (i + 2 < nkb) fetch_sz(i + 2, s2n, zlon, zhin);   // prefetch the next block's scale / zero-point
+    uint32_t s2 = 0, zlo = 0, zhi = 0;
+    for (int i = dg; i < nkb; i += DG) {
+      fetch_sz(i, s2, zlo, zhi);
       const int s = i % WST, ta = i % AST;
-      mbar_wait(full_w(s), ((uint32_t)(i / WST)) & 1u);
+      if (p.debug != 6) mbar_wait(full_w(s), ((uint32_t)(i / WST)) & 1u);
       const uint32_t* wsm = reinterpret_cast<const uint32_t*>(base_ptr + s * W_STAGE_BYTES) + nl;
       uint32_t wd[8];
+      if (p.debug >= 5) {
+#pragma unroll
+        for (int kw = 0; kw < 8; ++kw) wd[kw] = 0;
+      } else
 #pragma unroll
       for (int kw = 0; kw < 8; ++kw) wd[kw] = wsm[kw * TMN];
-      mbar_arrive(empty_w(s));                 // words are in registers
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_w(s));  // the warp's words are in registers (128 same-address arrivals serialise)
       uint32_t a[32];
+      if (p.debug >= 4) {   // measurement only: no dequant arithmetic
+#pragma unroll
+        for (int kw = 0; kw < 8; ++kw) a[4 * kw] = a[4 * kw + 1] = a[4 * kw + 2] = a[4 * kw + 3] = wd[kw];
+      } else
 #pragma unroll
       for (int kw = 0; kw < 8; ++kw) {
         const uint32_t w = wd[kw], w8 = w >> 8;
@@ -291,39 +309,73 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       mbar_wait(a_empty(ta), (((uint32_t)(i / AST)) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      tmem_st32(tmem_a0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ta * 32), a);
+      if (p.debug != 3 && p.debug < 5) tmem_st32(tmem_a0 + ((uint32_t)(q * 32) << 16) + (uint32_t)(ta * 32), a);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(a_full(ta));
-      s2 = s2n;
-      zlo = zlon;
-      zhi = zhin;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(a_full(ta));
     }
   } else {
-    // ---------------- epilogue warps
-    const int st = threadIdx.x - 10 * 32;      // 0..127
+    // ---------------- epilogue warps; lane 0 of the first one also produces the activation tiles, running as far ahead
+    // as its own ring allows (independent of the weight ring: coupling the two in one thread serialised every block's MMA
+    // behind an activation load that was issued one block earlier)
+    const int st = threadIdx.x - EPI_WARP0 * 32;      // 0..127
     const int q = warp & 3;
-    // ---- epilogue: lane quarter q, thread = out-channel n0 + 32 q + lane
-    mbar_wait(d_full, 0);
+    if (st == 0) {
+      if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (int i = 0; i < nkb; ++i) {
+        const int tb = i % bst;
+        mbar_wait(b_empty(tb), (((uint32_t)(i / bst)) & 1u) ^ 1u);
+        mbar_expect_tx(b_full(tb), b_stage_bytes);
+        tma_load_2d(b_ring + tb * b_stage_bytes, &map_x, b_full(tb), (kb0 + i) * KB, 0);
+      }
+    }
+    __syncwarp();
+    // ---- epilogue: lane quarter q, thread = out-channel n0 + 32 q + lane.  The accumulator is ready only at the very
+    // end: poll with a back-off instead of spinning 128 threads through the whole main loop
+    {
+      uint32_t done = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(d_full), "r"(0u)
+            : "memory");
+        if (!done) __nanosleep(256);
+      }
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int nl = q * 32 + lane, n = n0 + nl;
     const int splits = gridDim.y;
     const float bias = (p.bias && n < p.N) ? load_as_float(p.bias, p.bias_dtype, n) : 0.f;
+    auto load_acc = [&](int c, float (&acc)[16]) {   // sum of the independent accumulators, fixed order
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+#pragma unroll
+      for (int v = 0; v < 16; ++v) acc[v] = __uint_as_float(r[v]);
+      for (int a = 1; a < nacc; ++a) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * d_stride + (uint32_t)c, r);
+#pragma unroll
+        for (int v = 0; v < 16; ++v) acc[v] += __uint_as_float(r[v]);
+      }
+    };
     if (splits == 1) {
       for (int c = 0; c < NT; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        float acc[16];
+        load_acc(c, acc);
 #pragma unroll
         for (int v = 0; v < 16; ++v)
-          if (c + v < p.M) store_from_float(p.y, p.y_dtype, (int64_t)(c + v) * p.N + n, __uint_as_float(r[v]) + bias);
+          if (c + v < p.M) store_from_float(p.y, p.y_dtype, (int64_t)(c + v) * p.N + n, acc[v] + bias);
       }
     } else {
       float* mine = p.part_ws + ((size_t)(blockIdx.x * splits + blockIdx.y) * NT) * TMN + nl;
       for (int c = 0; c < NT; c += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+        float acc[16];
+        load_acc(c, acc);
 #pragma unroll
         for (int v = 0; v < 16; ++v)
-          if (c + v < p.M) mine[(size_t)(c + v) * TMN] = __uint_as_float(r[v]);
+          if (c + v < p.M) mine[(size_t)(c + v) * TMN] = acc[v];
       }
       __threadfence();
       asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -332,10 +384,18 @@ __global__ void __launch_bounds__(THREADS, 1)
       if (*flag_ptr == splits - 1) {   // last CTA of this tile: fixed-order sum over the splits
         __threadfence();
         const float* t0 = p.part_ws + ((size_t)(blockIdx.x * splits) * NT) * TMN + nl;
-        for (int m = 0; m < p.M; ++m) {
-          float acc = 0.f;
-          for (int s = 0; s < splits; ++s) acc += __ldcg(t0 + ((size_t)s * NT + m) * TMN);
-          store_from_float(p.y, p.y_dtype, (int64_t)m * p.N + n, acc + bias);
+        for (int mb = 0; mb < p.M; mb += 4) {       // 4 rows x all splits of loads in flight, summed in split order
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int s = 0; s < splits; ++s) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (mb + u < p.M) ? __ldcg(t0 + ((size_t)s * NT + mb + u) * TMN) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] += v[u];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (mb + u < p.M) store_from_float(p.y, p.y_dtype, (int64_t)(mb + u) * p.N + n, acc[u] + bias);
         }
         if (st == 0) p.counters[blockIdx.x] = 0;
       }
@@ -435,6 +495,8 @@ int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, 
   p.x = x; p.x_dtype = x_dtype; p.M = (int)M; p.K = (int)K; p.N = (int)N; p.g = g; p.G = (int)(K / g);
   p.qzeros = qzeros; p.scales = scales; p.bias = bias; p.bias_dtype = bias_dtype; p.input_scale = input_scale;
   p.y = y; p.y_dtype = y_dtype; p.pdl = pdl;
+  static const int dbg = getenv("B200WOQ_TC_DEBUG") ? atoi(getenv("B200WOQ_TC_DEBUG")) : 0;
+  p.debug = dbg;
   int splits;
   woq_tc_plan(M, N, K, &p.NT, &splits, &p.kb_per_split);
   p.counters = (int*)workspace;
@@ -442,7 +504,8 @@ int woq_tc_forward(const void* x, int x_dtype, int64_t M, int64_t K, int64_t N, 
   p.part_ws = (float*)((uint8_t*)workspace + ((tiles * 4 + 255) / 256) * 256);
   // instruction descriptor: D = F32 (1), A = B = F16 (0), both K-major, N = NT, M = 128
   const uint32_t idesc = (1u << 4) | ((uint32_t)(p.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  const size_t smem = (size_t)WST * W_STAGE_BYTES + (size_t)BST * 128 * 128 + 512 + 1024;
+  const size_t groups_max = (size_t)ceil_div((int64_t)p.kb_per_split * KB, g) + 1;
+  const size_t smem = (size_t)WST * W_STAGE_BYTES + (size_t)4 * 128 * 128 + 2048 + 1024 + groups_max * TMN * 3 + 256;
   WOQ_CUDA(cudaFuncSetAttribute(woq_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)tiles, (unsigned)splits);

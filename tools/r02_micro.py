@@ -95,7 +95,10 @@ def woq_tc():
     import math
 
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
-    for (N, K) in ((4096, 4096), (12288, 4096), (22016, 4096), (4096, 11008)):
+    shapes = ((4096, 4096), (12288, 4096), (22016, 4096), (4096, 11008))
+    if os.environ.get("B200WOQ_MICRO_SHAPES"):
+        shapes = [tuple(int(v) for v in t.split("x")) for t in os.environ["B200WOQ_MICRO_SHAPES"].split(",")]
+    for (N, K) in shapes:
         copies = min(48, max(4, int(math.ceil(300e6 / (N * K / 2)))))
         packs = []
         for i in range(copies):
@@ -103,7 +106,7 @@ def woq_tc():
             r = ops.rtn_quant_pack(W, 4, 128, True)
             packs.append((r["qweight"], r["qzeros"], r["scales"]))
             del W
-        for M in (8, 16, 32, 64, 128):
+        for M in [int(v) for v in os.environ.get("B200WOQ_MICRO_MS", "8,16,32,64,128").split(",")]:
             x = torch.randn(M, K, device=DEV, dtype=torch.float16)
             y = torch.empty(M, N, device=DEV, dtype=torch.float16)
 
