@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
     }
-    mbar_init(d_full, 1);
+    mbar_init(d_full, 2);       // both MMA issuers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -216,12 +216,20 @@ __global__ void __launch_bounds__(THREADS, 1)
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   {
+    // one vectorised round trip: per group 16 x 16-byte pieces of scales and 16 zero-point words (8 nibbles each)
     const int Nw = p.N >> 3;
-    for (int idx = threadIdx.x; idx < n_groups * TMN; idx += THREADS) {
-      const int gl = idx >> 7, nl = idx & 127, n = n0 + nl;
-      sc_tab[idx] = p.scales[(int64_t)(g_first + gl) * p.N + n];
-      const uint32_t zw = (uint32_t)p.qzeros[(int64_t)(g_first + gl) * Nw + (n >> 3)];
-      z_tab[idx] = (uint8_t)((((zw >> (4 * (n & 7))) & 0xfu) + 1u) & 0xfu);   // stored minus one (modules.py:363, 409-410)
+    for (int idx = threadIdx.x; idx < n_groups * 16; idx += THREADS) {
+      const int gl = idx >> 4, pc = idx & 15;
+      const uint4 sv = *reinterpret_cast<const uint4*>(p.scales + (int64_t)(g_first + gl) * p.N + n0 + pc * 8);
+      *reinterpret_cast<uint4*>(sc_tab + gl * TMN + pc * 8) = sv;
+      const uint32_t zw = (uint32_t)p.qzeros[(int64_t)(g_first + gl) * Nw + (n0 >> 3) + pc];
+      uint32_t lo = 0, hi = 0;   // stored minus one (modules.py:363, 409-410): +1 and wrap to 4 bits
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        lo |= ((((zw >> (4 * e)) & 0xfu) + 1u) & 0xfu) << (8 * e);
+        hi |= ((((zw >> (4 * (e + 4))) & 0xfu) + 1u) & 0xfu) << (8 * e);
+      }
+      *reinterpret_cast<uint2*>(z_tab + gl * TMN + pc * 8) = make_uint2(lo, hi);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -229,6 +237,29 @@ __global__ void __launch_bounds__(THREADS, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot_ptr;
   const uint32_t tmem_a0 = tmem_base + d_cols;   // A stages behind the accumulator columns
+
+  // One issuing thread spends ~600 cycles per 64-k block (two mbarrier waits at ~90 cycles each even when complete, four
+  // tiny MMAs at ~66 cycles of issue each, two commits): measured as THE serial bottleneck of the pipeline.  Two issuers
+  // take alternate blocks and own disjoint accumulators, so no ordering between them is needed.
+  auto mma_role = [&](int r) {
+    for (int i = r; i < nkb; i += 2) {
+      const int ta = i % AST, tb = i % bst;
+      mbar_wait(a_full(ta), ((uint32_t)(i / AST)) & 1u);
+      mbar_wait(b_full(tb), ((uint32_t)(i / bst)) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sb = b_ring + tb * b_stage_bytes;
+#pragma unroll
+      for (int k4 = 0; k4 < KB / 16; ++k4) {
+        const int acc = (nacc == 4) ? 2 * r + (k4 & 1) : r;
+        const bool first = (i == r) && (nacc == 4 ? k4 < 2 : k4 == 0);
+        umma_f16_ts(tmem_base + (uint32_t)acc * d_stride, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8), make_desc_k(sb + k4 * 32), idesc,
+                    first ? 0u : 1u);
+      }
+      umma_commit(a_empty(ta));
+      umma_commit(b_empty(tb));
+    }
+    umma_commit(d_full);
+  };
 
   if (warp == 0) {
     // ---------------- TMA producer of the packed weights (constants: no dependency on the previous kernel)
@@ -241,23 +272,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ---------------- MMA issuer
-    if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
-        const int ta = i % AST, tb = i % bst;
-        mbar_wait(a_full(ta), ((uint32_t)(i / AST)) & 1u);
-        mbar_wait(b_full(tb), ((uint32_t)(i / bst)) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sb = b_ring + tb * b_stage_bytes;
-#pragma unroll
-        for (int k4 = 0; k4 < KB / 16; ++k4)
-          umma_f16_ts(tmem_base + (uint32_t)(k4 & (nacc - 1)) * d_stride, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8),
-                      make_desc_k(sb + k4 * 32), idesc, (i > 0 || k4 >= nacc) ? 1u : 0u);
-        umma_commit(a_empty(ta));
-        umma_commit(b_empty(tb));
-      }
-      umma_commit(d_full);
-    }
+    // ---------------- MMA issuer 0 (even blocks); issuer 1 (odd blocks) is lane 0 of the second epilogue warp
+    if (lane == 0) mma_role(0);
   } else if (warp < EPI_WARP0) {
     // ---------------- dequant: group dg handles blocks i = dg, dg + 2, ...; thread = out-channel row
     const int dg = (warp - 2) >> 2;            // 0 .. DG-1
@@ -329,6 +345,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         tma_load_2d(b_ring + tb * b_stage_bytes, &map_x, b_full(tb), (kb0 + i) * KB, 0);
       }
     }
+    if (st == 32) mma_role(1);   // second MMA issuer (odd blocks)
     __syncwarp();
     // ---- epilogue: lane quarter q, thread = out-channel n0 + 32 q + lane.  The accumulator is ready only at the very
     // end: poll with a back-off instead of spinning 128 threads through the whole main loop
@@ -354,7 +371,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
 #pragma unroll
       for (int v = 0; v < 16; ++v) acc[v] = __uint_as_float(r[v]);
-      for (int a = 1; a < nacc; ++a) {
+      const int nacc_used = (nkb >= 2) ? nacc : nacc / 2;
+      for (int a = 1; a < nacc_used; ++a) {
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * d_stride + (uint32_t)c, r);
 #pragma unroll
         for (int v = 0; v < 16; ++v) acc[v] += __uint_as_float(r[v]);
