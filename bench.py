@@ -144,7 +144,9 @@ def run_b200(args):
     lib = _lib.load()
     pk = peaks()
     W, K = args.warmup, args.steps
-    wall = full_model_wall(dev, rank, world) if args.wall else None
+    # the un-warmed whole-model wall clock is a single-GPU user-experience number; at N > 1 it mostly measures how long N
+    # processes take to page CUDA libraries in on a fresh box (165 s first block at N = 8 on a cold image), so it is skipped
+    wall = full_model_wall(dev, rank, world) if (args.wall and world == 1) else None
     # every step is one decoder block of identical shape, so the steady-state run simply builds as many blocks as it
     # consumes: W warm-up + K timed + 1 for the phase breakdown + Ke for the host-resident (e2e) leg
     Ke = max(1, min(K, 6)) if args.e2e else 0

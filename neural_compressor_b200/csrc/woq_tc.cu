@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(b_full(s), 1);
       mbar_init(b_empty(s), 1);
     }
-    mbar_init(d_full, 2);       // both MMA issuers
+    mbar_init(d_full, NT <= 64 ? 4 : 2);   // every MMA issuer commits once at the end
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -240,21 +240,19 @@ __global__ void __launch_bounds__(THREADS, 1)
 
   // One issuing thread spends ~600 cycles per 64-k block (two mbarrier waits at ~90 cycles each even when complete, four
   // tiny MMAs at ~66 cycles of issue each, two commits): measured as THE serial bottleneck of the pipeline.  Two issuers
-  // take alternate blocks and own disjoint accumulators, so no ordering between them is needed.
+  // take alternate blocks and own disjoint accumulators, so no ordering between them is needed.  `nacc` issuers (4 for
+  // batch tiles <= 64, 2 for 128): issuer r = block index mod nacc, accumulator r.
   auto mma_role = [&](int r) {
-    for (int i = r; i < nkb; i += 2) {
+    for (int i = r; i < nkb; i += nacc) {
       const int ta = i % AST, tb = i % bst;
       mbar_wait(a_full(ta), ((uint32_t)(i / AST)) & 1u);
       mbar_wait(b_full(tb), ((uint32_t)(i / bst)) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t sb = b_ring + tb * b_stage_bytes;
 #pragma unroll
-      for (int k4 = 0; k4 < KB / 16; ++k4) {
-        const int acc = (nacc == 4) ? 2 * r + (k4 & 1) : r;
-        const bool first = (i == r) && (nacc == 4 ? k4 < 2 : k4 == 0);
-        umma_f16_ts(tmem_base + (uint32_t)acc * d_stride, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8), make_desc_k(sb + k4 * 32), idesc,
-                    first ? 0u : 1u);
-      }
+      for (int k4 = 0; k4 < KB / 16; ++k4)
+        umma_f16_ts(tmem_base + (uint32_t)r * d_stride, tmem_a0 + (uint32_t)(ta * 32 + k4 * 8), make_desc_k(sb + k4 * 32), idesc,
+                    (i == r && k4 == 0) ? 0u : 1u);
       umma_commit(a_empty(ta));
       umma_commit(b_empty(tb));
     }
@@ -345,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         tma_load_2d(b_ring + tb * b_stage_bytes, &map_x, b_full(tb), (kb0 + i) * KB, 0);
       }
     }
-    if (st == 32) mma_role(1);   // second MMA issuer (odd blocks)
+    if ((st & 31) == 0 && st > 0 && (st >> 5) < nacc) mma_role(st >> 5);   // MMA issuers 1..nacc-1 (lane 0 of epilogue warps 1..3)
     __syncwarp();
     // ---- epilogue: lane quarter q, thread = out-channel n0 + 32 q + lane.  The accumulator is ready only at the very
     // end: poll with a back-off instead of spinning 128 threads through the whole main loop
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
 #pragma unroll
       for (int v = 0; v < 16; ++v) acc[v] = __uint_as_float(r[v]);
-      const int nacc_used = (nkb >= 2) ? nacc : nacc / 2;
+      const int nacc_used = min(nacc, nkb);
       for (int a = 1; a < nacc_used; ++a) {
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)a * d_stride + (uint32_t)c, r);
 #pragma unroll

@@ -11,10 +11,7 @@ timeout 300 $FULL -k regex:hessian_syrk_tc2 -s 1 -c 1 -o $O/${R}_syrk_tc_4096 py
 timeout 300 $FULL -k regex:hessian_syrk_tc2 -s 4 -c 1 -o $O/${R}_syrk_tc_11008 python tools/prof_r02.py syrk > $O/${R}_ncu2.log 2>&1
 timeout 300 $FULL -k regex:potrf_inv_tile -s 3 -c 1 -o $O/${R}_k2_diag_tile python tools/prof_r02.py k2 4096 > $O/${R}_ncu3.log 2>&1
 timeout 300 $FULL -k regex:chol_trail -s 2 -c 1 -o $O/${R}_k2_trail python tools/prof_r02.py k2 4096 > $O/${R}_ncu4.log 2>&1
-timeout 300 $FULL -k regex:woq_gemm_tc -s 3 -c 3 -o $O/${R}_woq_tc_M16 python tools/prof_r02.py woq_tc 16 > $O/${R}_ncu5.log 2>&1
-timeout 300 $FULL -k regex:woq_gemm_tc -s 3 -c 3 -o $O/${R}_woq_tc_M64 python tools/prof_r02.py woq_tc 64 > $O/${R}_ncu6.log 2>&1
-timeout 300 $FULL -k regex:w8a8_gemm -s 1 -c 2 -o $O/${R}_w8a8_M2048 python tools/prof_r02.py w8a8 2048 > $O/${R}_ncu7.log 2>&1
-timeout 300 $FULL -k regex:w8a8_gemm -s 1 -c 2 -o $O/${R}_w8a8_M16 python tools/prof_r02.py w8a8 16 > $O/${R}_ncu8.log 2>&1
-timeout 300 $FULL -k regex:woq_gemm_stream -s 30 -c 1 -o $O/${R}_gemv_stream_qkv python tools/prof_gemv.py 1 2 stream > $O/${R}_ncu9.log 2>&1
+timeout 300 $FULL -k regex:woq_gemm_tc -s 4 -c 1 -o $O/${R}_woq_tc_M16 python tools/prof_r02.py woq_tc 16 > $O/${R}_ncu5.log 2>&1
+timeout 300 $FULL -k regex:w8a8_gemm -s 4 -c 1 -o $O/${R}_w8a8_M2048 python tools/prof_r02.py w8a8 2048 > $O/${R}_ncu7.log 2>&1
 ls -la $O | grep ${R}_
 tail -2 $O/${R}_launches.log
