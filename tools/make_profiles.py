@@ -26,6 +26,8 @@ import ncu_summary  # noqa: E402
 
 
 NOTES = {
+    "r02": "Round 2: tools/profile_round2.sh.  Under ncu every launch is serialised with cold caches: the 128x128 diagonal-tile kernel of K2\n"
+           "shows 178 us here and ~85 us in the un-profiled factorisation (tools/r02_micro.py k2).\n",
     "r01": "This list was captured before the round's last two kernel changes (CTA-pair SYRK: -7 % per launch; 8-warp GPTQ\n"
            "column loop + 2-CTA/SM lazy update: -28 % per layer), so K1/K3 shares are slightly lower in the final build\n"
            "(step 460 -> 420 ms); the per-kernel captures next to this file are from the final build.\n",
@@ -53,7 +55,9 @@ def launch_share(rnd):
         agg[name][1] += v
         n += 1
     tot = sum(v[1] for v in agg.values())
-    ours = sum(v[1] for k, v in agg.items() if "b200woq" in k or "hessian_syrk_tc" in k)
+    OURS = ("b200woq", "hessian_syrk_tc", "cholinv::", "tc::", "woqtc::", "w8a8::", "stream::", "lazytc::")
+    ours = sum(v[1] for k, v in agg.items() if any(t in k for t in OURS))
+    libs = sum(v[1] for k, v in agg.items() if any(t in k for t in ("getrf", "trsm", "xxtrf", "cusolver")))
     with open(os.path.join(ROOT, "profiles", f"{rnd}_step_share.md"), "w") as f:
         f.write(f"# {rnd}: kernel share of one timed step (one Llama-2-7B decoder block of GPTQ calibration)\n\n")
         f.write("Source: `ncu --metrics gpu__time_duration.sum --clock-control none --nvtx --nvtx-include \"timed_steps/\"` around\n"
@@ -61,7 +65,9 @@ def launch_share(rnd):
                 f"launch list is `{rnd}_launches.csv.gz`.  Durations are serialised, cold-cache per-launch times: read the SHARES.\n"
                 + NOTES.get(rnd, "") + "\n")
         f.write(f"{n} launches, {tot:.1f} ms of kernel time; hand-written b200woq kernels: {ours:.1f} ms ({100 * ours / tot:.1f} %), the rest is\n"
-                "the model's own forward (cuBLAS `nvjet` GEMMs, SDPA, torch elementwise) and cuSOLVER/cuBLAS inside the Cholesky chain.\n\n")
+                "the model's own forward (cuBLAS `nvjet` GEMMs, SDPA, torch elementwise)"
+                + (f"; cuSOLVER/cuBLAS factorisation kernels: {libs:.1f} ms.\n\n" if rnd == "r01" or libs > 0 else
+                   "; NO cuSOLVER / cuBLAS-trsm kernel is left in the step (K2 is hand-written).\n\n"))
         f.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
             f.write(f"| `{k}` | {v[0]} | {v[1]:.2f} | {100 * v[1] / tot:.1f} % |\n")
