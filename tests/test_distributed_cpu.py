@@ -68,7 +68,7 @@ def _rows_worker(rank, world, port, ret):
     full = lay.fasterquant(W, 128, 0.01, 32)
     hinv = full["hinv"]
 
-    def fake_fasterquant(Wp, Hinv, dead, blocksize, groupsize, bits, sym, mse, want_q=True):
+    def fake_fasterquant(Wp, Hinv, dead, blocksize, groupsize, bits, sym, mse, want_q=True, double_quant=None):
         # stand-in for the CUDA column loop: the oracle on this rank's rows (the product path never does this)
         sub = O.GPTQLayerOracle(Wp.shape[0], C, bits=bits, sym=sym).fasterquant(Wp, blocksize, 0.01, groupsize, hinv=Hinv)
         codes = (O.GPTQLayerOracle.export_codes(sub["Q"], sub["scale"], sub["zero"], groupsize, sym) + 8).to(torch.uint8)
