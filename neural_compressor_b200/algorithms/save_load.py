@@ -116,6 +116,15 @@ def _load_huggingface(model_dir, device="cuda", **kwargs):
     model = model.to(device)
     for name, mod in list(model.named_modules()):
         if isinstance(mod, torch.nn.Linear) and (name + ".qweight") in state:
+            qw = state[name + ".qweight"]
+            if tuple(qw.shape) == (mod.in_features, mod.out_features // 8) and bits == 4:
+                # AutoAWQ GEMM layout (packed along out_features, interleaved nibble order): repack to the optimum format
+                # like the reference does at load time (transformers/quantization/utils.py:702, utility.py:1432-1459)
+                from .awq_repack import repack_awq_to_optimum_format
+
+                g_ = group_size if group_size > 0 else mod.in_features
+                state[name + ".qweight"], state[name + ".qzeros"], state[name + ".scales"] = repack_awq_to_optimum_format(
+                    qw, state[name + ".qzeros"], state[name + ".scales"], bits, g_)
             g = group_size if group_size > 0 else mod.in_features
             new = B200WeightOnlyLinear(mod.in_features, mod.out_features, dtype="int", bits=bits, group_size=g,
                                        zp=True, bias=(name + ".bias") in state,

@@ -391,7 +391,21 @@ def gen_hf_config():
     print("hf_config:", cases)
 
 
-GENERATORS_EXTRA = {"options_extra": gen_options_extra}
+def gen_awq_repack():
+    """AutoAWQ -> optimum repack (utility.py:1432-1459) on random packed tensors: a pure nibble permutation."""
+    from neural_compressor.torch.algorithms.weight_only.utility import repack_awq_to_optimum_format
+
+    g = torch.Generator().manual_seed(0)
+    K, N, gs = 256, 64, 32
+    qw = torch.randint(-2**31, 2**31 - 1, (K, N // 8), generator=g, dtype=torch.int64).to(torch.int32)
+    qz = torch.randint(-2**31, 2**31 - 1, (K // gs, N // 8), generator=g, dtype=torch.int64).to(torch.int32)
+    sc = (torch.rand(K // gs, N, generator=g) * 0.02 + 0.005).half()
+    a = repack_awq_to_optimum_format(qw, qz, sc, 4, gs)
+    torch.save(dict(awq_qweight=qw, awq_qzeros=qz, awq_scales=sc, group_size=gs, qweight=a[0], qzeros=a[1], scales=a[2]),
+               os.path.join(OUT, "awq_repack.pt"))
+
+
+GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack}
 
 if __name__ == "__main__":
     load_reference()
@@ -414,3 +428,5 @@ if __name__ == "__main__":
             gen_options()
         if "options_extra" in which:
             gen_options_extra()
+        if "awq_repack" in which:
+            gen_awq_repack()

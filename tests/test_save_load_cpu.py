@@ -84,3 +84,18 @@ def test_hf_quant_config_matches_reference_fixture():
         if tag == "gptq":
             mapping[("lm_head", "Linear")] = q.GPTQConfig(dtype="fp32")
         assert change_config_to_hf_format(mapping) == case["out"], tag
+
+
+def test_awq_repack_matches_reference_fixture():
+    """f1: AutoAWQ GEMM layout -> optimum format (utility.py:1432-1459); the fixture was written by the live reference's
+    `repack_awq_to_optimum_format` (oracle/gen_golden.py awq_repack).  Pure integer tensor ops: runs on the host."""
+    import os
+
+    import torch
+
+    from neural_compressor_b200.algorithms.awq_repack import repack_awq_to_optimum_format
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "awq_repack.pt"))
+    qw, qz, sc = repack_awq_to_optimum_format(g["awq_qweight"], g["awq_qzeros"], g["awq_scales"], 4, g["group_size"])
+    assert torch.equal(qw, g["qweight"]) and torch.equal(qz, g["qzeros"]) and torch.equal(sc, g["scales"])
+    assert qw.dtype == torch.int32 and tuple(qw.shape) == (g["awq_qweight"].shape[0] // 8, g["awq_qweight"].shape[1] * 8)
