@@ -64,17 +64,64 @@ def build_layer_sharded(factory: Callable[[], torch.nn.Module], blocks_attr: str
     lo, hi = block_range(rank, world, n)
     block_ids = {id(b) for b in blocks}
 
-    def materialise(mod, idx):
+    def materialise(mod, idx, path):
         mod.to_empty(device=device)
+        mod._b200_path = path   # qualified name, for checkpoint-backed `init` callables (checkpoint_init)
         (init or (lambda m, i: _random_fill(m, seed * 100003 + i + 1)))(mod, idx)
 
     # non-block modules (embeddings, final norm, head, rotary tables): replicated
     for name, child in list(model.named_children()):
         _materialise_outside(child, name, blocks_attr, block_ids, materialise)
     for i in range(lo, hi):
-        materialise(blocks[i], i)
+        materialise(blocks[i], i, f"{blocks_attr}.{i}")
     model._b200_shard = dict(rank=rank, world=world, n_blocks=n, blocks_attr=blocks_attr, owned=(lo, hi))
     return model
+
+
+def checkpoint_init(model_path: str, tied: Optional[dict] = None):
+    """`init` callable for `build_layer_sharded` that fills a materialised module from a HuggingFace safetensors
+    checkpoint directory (single file or sharded with `model.safetensors.index.json`), reading only the tensors of that
+    module -- each rank touches its own blocks plus the replicated embeddings / head, never the whole checkpoint.
+    `tied` maps a parameter absent from the file to the one it is tied to (default: lm_head.weight ->
+    model.embed_tokens.weight, the `tie_word_embeddings` case)."""
+    import json
+    import os
+
+    from safetensors import safe_open
+
+    tied = {"lm_head.weight": "model.embed_tokens.weight"} if tied is None else tied
+    index_file = os.path.join(model_path, "model.safetensors.index.json")
+    if os.path.exists(index_file):
+        with open(index_file) as f:
+            where = json.load(f)["weight_map"]
+    else:
+        single = os.path.join(model_path, "model.safetensors")
+        with safe_open(single, framework="pt") as f:
+            where = {k: "model.safetensors" for k in f.keys()}
+    handles = {}
+
+    def read(name):
+        if name not in where:
+            if name in tied and tied[name] in where:
+                name = tied[name]
+            else:
+                raise KeyError(f"{name} is not in the checkpoint at {model_path}")
+        fn = where[name]
+        if fn not in handles:
+            handles[fn] = safe_open(os.path.join(model_path, fn), framework="pt")
+        return handles[fn].get_tensor(name)
+
+    def init(mod, idx):
+        prefix = mod._b200_path
+        for name, p in mod.named_parameters():
+            p.data.copy_(read(f"{prefix}.{name}"))
+        persistent = {n for n, _ in mod.named_buffers()} - {
+            (mn + "." if mn else "") + b for mn, m in mod.named_modules() for b in getattr(m, "_non_persistent_buffers_set", ())}
+        for name, b in mod.named_buffers():
+            if name in persistent:
+                b.data.copy_(read(f"{prefix}.{name}"))
+
+    return init
 
 
 def _materialise_outside(module, path, blocks_attr, block_ids, materialise):
@@ -89,7 +136,7 @@ def _materialise_outside(module, path, blocks_attr, block_ids, materialise):
         if own:
             raise NotImplementedError(f"{path} holds tensors next to the transformer stack")
         return
-    materialise(module, -1)
+    materialise(module, -1, path)
     _restore_buffers(module)
 
 
