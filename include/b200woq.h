@@ -98,6 +98,39 @@ int b200woq_dequantize(const int32_t* qweight, const int32_t* qzeros, const void
                        const int32_t* g_idx, int64_t N, int64_t K, int bits, int group_size,
                        void* w_fp16_out, void* stream);
 
+/* ---- 4-bit TABLE data types: nf4, fp4 (= fp4_e2m1_bnb), fp4_e2m1 (utility.py:52-103) ------------------------- */
+
+/* One data type = its ascending levels (FLOAT_MAPPING), the integer code the reference stores for each level
+ * (INT_MAPPING), the mid points between neighbours ((level[i] + level[i+1]) / 2 evaluated in double, then converted to
+ * float like torch converts a Python scalar) and max(levels).  HOST struct, passed by pointer, read at call time. */
+typedef struct {
+  int32_t n;          /* number of levels: 16 (nf4) or 15 (fp4 variants) */
+  float level[16];
+  float mid[16];      /* n - 1 entries */
+  int32_t code[16];   /* in [-8, 7] */
+  float max_level;
+} b200woq_f4_table;
+
+/* quantize_4bit (utility.py:121-160) under quant_tensor's grouping (utility.py:272-376, ragged tail group included):
+ * scale = absmax(group) * quantile / max_level, element -> nearest level by the mid-point intervals, every op rounded
+ * through W's dtype like torch does.  Outputs (each may be NULL, at least one is required):
+ *   codes_out int8 [N,K]   the integer codes quant_tensor(return_int=True) leaves in the tensor
+ *   scale_out fp32 [N,G]   the scales (exactly the W-dtype values)
+ *   fake_out  w_dtype [N,K] level * scale, i.e. quant_tensor(return_int=False); may alias W. */
+int b200woq_f4_quantize(const void* W, int w_dtype, int64_t N, int64_t K, int group_size,
+                        const b200woq_f4_table* host_table, float quantile, int8_t* codes_out, float* scale_out,
+                        void* fake_out, void* stream);
+
+/* INCWeightOnlyLinear.pack for the non-optimum layout with compression_dim = 1, int32 (modules.py:352-357, 445-466):
+ * qweight[n, j] = OR_e (codes[n, j*n_pack + e] & mask) << bits*e, qweight int32 [N, ceil(K/n_pack)]. */
+int b200woq_pack_rows(const int8_t* codes, int64_t N, int64_t K, int bits, int32_t* qweight_out, void* stream);
+
+/* unpack + recover for a table data type (modules.py:377-443): nibble -> host_nibble_levels[nibble] (16 floats indexed
+ * by the stored 4-bit field, i.e. the level of the sign-extended code, 0 for unused codes) times scales fp32 [N,G];
+ * w_out fp32 [N,K]. */
+int b200woq_f4_dequantize(const int32_t* qweight, const float* scales, const float* host_nibble_levels, int64_t N,
+                          int64_t K, int group_size, float* w_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K6  WeightOnlyLinear.forward: fused unpack + dequant + matmul (modules.py:594-610)
  * ---------------------------------------------------------------------------------------------- */

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200woq.so")
-SOURCES = ["api.cu", "rtn_pack.cu", "woq_gemm.cu", "woq_stream.cu", "woq_tc.cu", "hessian.cu", "hessian_tc.cu", "cholinv.cu", "gptq.cu", "gptq_tc.cu", "stats.cu", "w8a8.cu"]
+SOURCES = ["api.cu", "rtn_pack.cu", "float4.cu", "woq_gemm.cu", "woq_stream.cu", "woq_tc.cu", "hessian.cu", "hessian_tc.cu", "cholinv.cu", "gptq.cu", "gptq_tc.cu", "stats.cu", "w8a8.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

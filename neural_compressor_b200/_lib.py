@@ -31,6 +31,10 @@ _SIGS = {
     "b200woq_unpack": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "b200woq_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int,
                                    c_void_p, c_void_p]),
+    "b200woq_f4_quantize": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_void_p]),
+    "b200woq_pack_rows": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "b200woq_f4_dequantize": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "b200woq_linear_workspace_bytes": (c_int64, [c_int64, c_int64, c_int64, c_int, c_int]),
     "b200woq_linear_forward": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
                                        c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

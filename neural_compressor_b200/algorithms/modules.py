@@ -59,14 +59,24 @@ class WeightOnlyLinear(torch.nn.Module):
 class B200WeightOnlyLinear(WeightOnlyLinear):
     """Drop-in for `INCWeightOnlyLinear(use_optimum_format=True)` with the kernels on the B200."""
 
+    def __new__(cls, in_features=None, out_features=None, dtype="int", *args, **kwargs):
+        """The reference's class covers two layouts behind one constructor.  The optimum format (the default, the only
+        one GPTQ / AWQ / int RTN produce and the one the dequant-GEMM kernels read) is this class; the non-optimum
+        layout -- `use_optimum_format=False`, which the table data types nf4 / fp4 force (modules.py:214-222) -- is
+        `modules_rowmajor.B200RowMajorLinear`, returned from here so that callers keep the reference's constructor."""
+        if cls is B200WeightOnlyLinear and ("int" not in str(dtype) or not kwargs.get("use_optimum_format", True)):
+            from .modules_rowmajor import B200RowMajorLinear
+
+            return B200RowMajorLinear(in_features, out_features, dtype, *args, **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, in_features, out_features, dtype="int", bits=4, group_size=32, zp=False, bias=False,
                  scale_dtype=torch.float32, compression_dtype=torch.int32, compression_dim=1, g_idx=False,
                  device="cuda", use_optimum_format=True, **kwargs):
         super().__init__(in_features, out_features, dtype, bits, group_size, device, scale_dtype=scale_dtype)
-        if "int" not in str(dtype):
-            raise NotImplementedError("nf4/fp4 tables are not on the B200 hot path (SURVEY §8 f3)")
-        if not use_optimum_format or compression_dtype != torch.int32:
-            raise NotImplementedError("only the default optimum format (int32, K-major) has B200 kernels")
+        # `compression_dtype` / `compression_dim` / `scale_dtype` are ignored in the optimum format, as in the reference
+        # (modules.py:241-262 forces int32 words packed along K and fp16 scales)
+        assert "int" in str(dtype) and use_optimum_format, "routed to B200RowMajorLinear by __new__"
         self.use_optimum_format = True
         self.compression_dtype = torch.int32
         self.float_type = torch.float16

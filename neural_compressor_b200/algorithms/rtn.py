@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from .. import ops
+from .. import dtypes, ops
 from ..utils import current_device, get_model_device, logger, set_module
 from .base_algorithm import Quantizer
 from .modules import B200WeightOnlyLinear
@@ -27,17 +27,47 @@ def _supported_layers():
     return tuple(types)
 
 
-def search_clip(weight: torch.Tensor, bits=4, group_size=32, scheme="asym", enable_full_range=False) -> float:
+def search_clip(weight: torch.Tensor, bits=4, group_size=32, scheme="asym", enable_full_range=False, dtype="int") -> float:
     """utility.py:439-480: 40 ratios 1 - i/200, loss = mean((W - qdq(W))^2) over the whole tensor."""
     best_err, best = float("inf"), None
     tmp = torch.empty_like(weight)
     for i in range(int(0.2 * 200)):
         ratio = 1 - i / 200
-        ops.rtn_fake_quant(weight, bits, group_size, scheme == "sym", enable_full_range, ratio, out=tmp)
+        if dtypes.is_table_dtype(dtype):
+            ops.f4_quantize(weight, dtype, group_size, ratio, want_codes=False, fake_out=tmp)
+        else:
+            ops.rtn_fake_quant(weight, bits, group_size, scheme == "sym", enable_full_range, ratio, out=tmp)
         loss = (weight - tmp).float().pow(2).mean()
         if loss < best_err:
             best_err, best = loss, ratio
     return best
+
+
+def cast_fp8(weight: torch.Tensor, dtype: str) -> torch.Tensor:
+    """utility.py:163-172 (`use_qdq=True`): round the weight through an fp8 storage type in place; no scaling, the module
+    stays a Linear.  A pure dtype round trip on the device."""
+    fp8 = getattr(torch, dtype.replace("fp8", "float8"))
+    weight.copy_(weight.to(fp8).to(weight.dtype))
+    return weight
+
+
+def double_quant_scales(scale: torch.Tensor, w_dtype: torch.dtype, cfg: dict) -> torch.Tensor:
+    """quant_tensor's second level (utility.py:377-434): the [N, G] scales, flattened row-major to one row, are
+    fake-quantised in groups of `double_quant_group_size` (symmetric `double_quant_bits`-bit; the "asym" scheme first
+    subtracts the mean of all scales and adds it back).  Arithmetic runs in the weight's dtype, like the reference's
+    `scale` tensor.  `scale` is the fp32 [N, G] tensor of the K4 kernels (holding exactly the weight-dtype values)."""
+    if str(cfg.get("double_quant_dtype", "int")) != "int":
+        raise NotImplementedError("double quant of scales: int dtype only")
+    flat = scale.to(w_dtype).reshape(1, -1).contiguous()
+    asym = cfg.get("double_quant_scheme", "asym") == "asym"
+    if asym:
+        mean = flat.mean()
+        flat.sub_(mean)
+    ops.rtn_fake_quant(flat, int(cfg.get("double_quant_bits", 8)), int(cfg.get("double_quant_group_size", 256)), True, False,
+                       1.0, out=flat)
+    if asym:
+        flat.add_(mean)
+    return flat.reshape(scale.shape).float()
 
 
 class RTNQuantizer(Quantizer):
@@ -73,8 +103,10 @@ class RTNQuantizer(Quantizer):
             dtype = cfg.get("dtype", "int")
             if dtype == "fp32":
                 continue
-            if dtype in ("fp8_e5m2", "fp8_e5m2fnuz", "fp8_e4m3fn", "fp8_e4m3fnuz", "nf4", "fp4", "fp4_e2m1", "fp4_e2m1_bnb"):
-                raise NotImplementedError(f"dtype {dtype} is outside the B200 hot path (SURVEY §8 f3)")
+            if dtype in dtypes.FP8_DTYPES:   # rtn.py:166-170: qdq cast, the module stays a Linear on the device
+                m.to(device)
+                cast_fp8(m.weight.data, dtype)
+                continue
             bits = cfg.get("bits", 4)
             if dtype != "int" and "int" in dtype:
                 bits = int(dtype.lstrip("int"))
@@ -85,8 +117,7 @@ class RTNQuantizer(Quantizer):
             group_dim = cfg.get("group_dim", 1)
             use_full_range = cfg.get("use_full_range", False)
             use_mse_search = cfg.get("use_mse_search", False)
-            if cfg.get("use_double_quant", False):
-                raise NotImplementedError("double quant of scales is outside the B200 hot path (SURVEY §8 f3)")
+            double_quant = bool(cfg.get("use_double_quant", False))
             is_conv1d = bool(conv1d) and isinstance(m, conv1d)
             transpose = (group_dim == 0) ^ is_conv1d   # rtn.py:209-216
             if group_dim == 0 and not is_conv1d:
@@ -94,15 +125,30 @@ class RTNQuantizer(Quantizer):
             w = m.weight.detach().to(device)
             w = w.t().contiguous() if transpose else w.contiguous()   # [N = out, K = in]
             if use_mse_search:
-                quantile = search_clip(w, bits, group_size, scheme, use_full_range)
-            r = ops.rtn_quant_pack(w, bits, group_size, scheme == "sym", use_full_range, quantile)
+                quantile = search_clip(w, bits, group_size, scheme, use_full_range, dtype)
+            k = w.shape[1]
+            if double_quant and k % (k if group_size == -1 or k < group_size else group_size) != 0:
+                double_quant = False   # quant_tensor returns from its ragged-tail branch before the second level (utility.py:334-373)
             if is_conv1d:
                 in_features, out_features = m.weight.shape[0], m.weight.shape[1]
             else:
                 in_features, out_features = m.in_features, m.out_features
-            new_module = B200WeightOnlyLinear(in_features, out_features, dtype=dtype, bits=bits, group_size=group_size,
-                                              zp=scheme != "sym", bias=m.bias is not None, device=device)
-            new_module.set_packed(r["qweight"], r["qzeros"], r["scales"], m.bias)
+            if dtypes.is_table_dtype(dtype):
+                # nf4 / fp4: nearest-level codes + absmax scales (float4.cu), packed along K into the non-optimum layout
+                # the reference forces for these types (modules.py:214-222); no zero points
+                r = ops.f4_quantize(w, dtype, group_size, quantile)
+                scale = double_quant_scales(r["scale"], w.dtype, cfg) if double_quant else r["scale"]
+                new_module = B200WeightOnlyLinear(in_features, out_features, dtype=dtype, bits=bits, group_size=group_size,
+                                                  zp=False, bias=m.bias is not None, device=device)
+                new_module.set_packed(ops.pack_rows(r["codes"], bits), scale, m.bias)
+            else:
+                r = ops.rtn_quant_pack(w, bits, group_size, scheme == "sym", use_full_range, quantile)
+                new_module = B200WeightOnlyLinear(in_features, out_features, dtype=dtype, bits=bits, group_size=group_size,
+                                                  zp=scheme != "sym", bias=m.bias is not None, device=device)
+                if double_quant:   # the codes keep the first-level scale; only the stored scales change (utility.py:377-434)
+                    scales16, _ = ops.pack_params(double_quant_scales(r["scale_f32"], w.dtype, cfg), r["zp_f32"], bits)
+                    r["scales"] = scales16
+                new_module.set_packed(r["qweight"], r["qzeros"], r["scales"], m.bias)
             if model_device.type == "cuda":
                 new_module.to(model_device)
             if name == "":

@@ -169,6 +169,7 @@ def load(model_name_or_path, original_model=None, format="default", device="cuda
     if format != "default":
         raise ValueError(f"unknown load format {format!r} (default | huggingface)")
     assert original_model is not None, "original_model is required for format='default'"
+    from ..dtypes import is_table_dtype
     from ..utils import fetch_module, set_module
     from .modules import B200WeightOnlyLinear, MulLinear
 
@@ -203,11 +204,19 @@ def load(model_name_or_path, original_model=None, format="default", device="cuda
         bits = cfg["bits"]
         if isinstance(cfg.get("dtype"), str) and cfg["dtype"] != "int" and cfg["dtype"].startswith("int"):
             bits = int(cfg["dtype"].lstrip("int"))
-        g = state[prefix + ".scales"].shape[0]
         group_size = cfg["group_size"] if cfg["group_size"] > 0 else in_f
-        new = B200WeightOnlyLinear(in_f, out_f, dtype="int", bits=bits, group_size=group_size,
-                                   zp=True, bias=True, g_idx=(prefix + ".g_idx") in state, device=device)
-        assert new.scales.shape[0] == g, f"{op_name}: {new.scales.shape[0]} groups expected, checkpoint has {g}"
+        if is_table_dtype(cfg.get("dtype", "int")):
+            # nf4 / fp4 modules live in the non-optimum layout: scales [N, G], no zero points (modules.py:214-222)
+            g = state[prefix + ".scales"].shape[1]
+            new = B200WeightOnlyLinear(in_f, out_f, dtype=cfg["dtype"], bits=bits, group_size=group_size, zp=False,
+                                       bias=(prefix + ".bias") in state, device=device)
+            groups = new.scales.shape[1]
+        else:
+            g = state[prefix + ".scales"].shape[0]
+            new = B200WeightOnlyLinear(in_f, out_f, dtype="int", bits=bits, group_size=group_size,
+                                       zp=True, bias=True, g_idx=(prefix + ".g_idx") in state, device=device)
+            groups = new.scales.shape[0]
+        assert groups == g, f"{op_name}: {groups} groups expected, checkpoint has {g}"
         if wrapped in state:
             new = MulLinear(new, torch.empty(in_f, device=device))
         set_module(model, op_name, new)

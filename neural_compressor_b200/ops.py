@@ -112,6 +112,60 @@ def dequantize(qweight, qzeros, scales, bits, group_size, in_features, out_featu
     return out
 
 
+# ------------------------------------------------------------------ 4-bit table data types (nf4 / fp4 / fp4_e2m1)
+def f4_quantize(W: torch.Tensor, dtype: str, group_size=-1, quantile=1.0, want_codes=True, fake_out=None):
+    """quant_tensor(dtype=nf4|fp4|...) (utility.py:121-160, 272-376).  Returns dict(codes int8 [N,K] | None,
+    scale fp32 [N,G]); with `fake_out` (same dtype / shape as W, may be W) also writes the fake-quantised weight."""
+    import ctypes
+
+    from . import dtypes
+
+    require_cuda(W, "W")
+    N, K = W.shape
+    G = math.ceil(K / _eff_group(K, group_size))
+    codes = torch.empty((N, K), dtype=torch.int8, device=W.device) if want_codes else None
+    scale = torch.empty((N, G), dtype=torch.float32, device=W.device)
+    if fake_out is not None:
+        require_cuda(fake_out, "fake_out")
+        if fake_out.dtype != W.dtype or fake_out.shape != W.shape:
+            raise _lib.B200WOQError("fake_out must match W")
+    table = dtypes.table(dtype)
+    check(_lib.load().b200woq_f4_quantize(ptr(W), dt(W), N, K, int(group_size), ctypes.c_void_p(ctypes.addressof(table)),
+                                          float(quantile), ptr(codes), ptr(scale), ptr(fake_out), stream_ptr(W.device)),
+          "f4_quantize")
+    return dict(codes=codes, scale=scale)
+
+
+def pack_rows(codes: torch.Tensor, bits: int):
+    """Signed / unsigned int8 codes [N,K] -> int32 [N, ceil(K/n_pack)], fields along K (modules.py:352-357, 445-466)."""
+    require_cuda(codes, "codes")
+    if codes.dtype != torch.int8:
+        raise _lib.B200WOQError("codes must be int8")
+    N, K = codes.shape
+    qweight = torch.empty((N, math.ceil(K / n_pack(bits))), dtype=torch.int32, device=codes.device)
+    check(_lib.load().b200woq_pack_rows(ptr(codes), N, K, bits, ptr(qweight), stream_ptr(codes.device)), "pack_rows")
+    return qweight
+
+
+def f4_dequantize(qweight: torch.Tensor, scales: torch.Tensor, dtype: str, group_size: int, in_features: int):
+    """recover() of a table-dtype module (modules.py:377-443): fp32 [N,K] = level(nibble) * scale."""
+    from . import dtypes
+
+    require_cuda(qweight, "qweight")
+    require_cuda(scales, "scales")
+    N = qweight.shape[0]
+    G = math.ceil(in_features / _eff_group(in_features, group_size))
+    if (qweight.dtype != torch.int32 or scales.dtype != torch.float32 or tuple(qweight.shape) != (N, math.ceil(in_features / 8))
+            or tuple(scales.shape) != (N, G)):
+        raise _lib.B200WOQError(f"f4_dequantize: qweight int32 [N, ceil(K/8)] and scales fp32 [N, G] expected, got "
+                                f"{qweight.dtype} {tuple(qweight.shape)}, {scales.dtype} {tuple(scales.shape)}")
+    out = torch.empty((N, in_features), dtype=torch.float32, device=qweight.device)
+    levels = dtypes.nibble_levels(dtype)
+    check(_lib.load().b200woq_f4_dequantize(ptr(qweight), ptr(scales), levels, N, in_features, int(group_size), ptr(out),
+                                            stream_ptr(qweight.device)), "f4_dequantize")
+    return out
+
+
 # ------------------------------------------------------------------ K6: fused dequant GEMM
 _WS_CACHE = {}
 

@@ -405,7 +405,80 @@ def gen_awq_repack():
                os.path.join(OUT, "awq_repack.pt"))
 
 
-GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack}
+RTN_DTYPE_CASES = [
+    # the reference's own RTN dtype matrix (test_rtn.py:269-300, 302-345): table data types, fp8 casts, double quant
+    ("rtn_nf4", dict(dtype="nf4")),
+    ("rtn_fp4", dict(dtype="fp4")),
+    ("rtn_fp4_e2m1_bnb", dict(dtype="fp4_e2m1_bnb", group_size=64)),
+    ("rtn_fp4_e2m1", dict(dtype="fp4_e2m1")),
+    ("rtn_nf4_mse", dict(dtype="nf4", use_mse_search=True, group_size=128)),
+    ("rtn_fp8_e4m3fn", dict(dtype="fp8_e4m3fn")),
+    ("rtn_fp8_e5m2", dict(dtype="fp8_e5m2")),
+    ("rtn_int4_dq_asym", dict(dtype="int4", use_double_quant=True, double_quant_bits=6, double_quant_use_sym=False,
+                              double_quant_group_size=256)),
+    ("rtn_int4_dq_sym", dict(dtype="int4", use_sym=False, use_double_quant=True, double_quant_bits=8,
+                             double_quant_use_sym=True, double_quant_group_size=8)),
+    ("rtn_nf4_dq", dict(dtype="nf4", use_double_quant=True, double_quant_bits=6, double_quant_use_sym=False,
+                        double_quant_group_size=256)),
+]
+
+
+def gen_rtn_dtypes():
+    """tests/golden/rtn_dtypes.pt: (1) quantize_4bit under quant_tensor's grouping on seeded tensors (utility.py:121-160,
+    272-376); (2) the non-optimum INCWeightOnlyLinear layouts of the reference's module test (test_woq_module.py:10-52:
+    bits x compression dtype, plus compression_dim 0 and the no-zero-point case); (3) tiny-llama RTN runs over the
+    reference's dtype matrix."""
+    import itertools
+
+    from neural_compressor.torch.algorithms.weight_only.modules import INCWeightOnlyLinear
+    from neural_compressor.torch.algorithms.weight_only.utility import quant_tensor
+    from neural_compressor.torch.quantization import RTNConfig, convert, prepare
+
+    g = torch.Generator().manual_seed(11)
+    out = dict(quant=[], rowmajor=[], models={})
+    for dtype, T, (n, k, gs), quantile in [("nf4", torch.float32, (32, 128, 32), 1.0), ("nf4", torch.float16, (16, 100, 32), 0.9),
+                                           ("nf4", torch.bfloat16, (16, 96, -1), 1.0), ("fp4", torch.float32, (16, 128, 32), 1.0),
+                                           ("fp4", torch.float16, (16, 128, 64), 0.95), ("fp4_e2m1", torch.float32, (16, 100, 32), 1.0),
+                                           ("fp4_e2m1", torch.bfloat16, (16, 128, 128), 0.805)]:
+        w = (torch.randn(n, k, generator=g) * 0.05).to(T)
+        w[1, :32] = 0                         # an all-zero group: scale 0, w / scale NaN -> code 0
+        codes, scale, _ = quant_tensor(w.clone(), dtype=dtype, group_size=gs, quantile=quantile, return_int=True)
+        fake = quant_tensor(w.clone(), dtype=dtype, group_size=gs, quantile=quantile, return_int=False)
+        out["quant"].append(dict(dtype=dtype, group_size=gs, quantile=quantile, W=w, codes=codes.to(torch.int8),
+                                 scale=scale.float(), fake=fake))
+    combos = [(b, cd, 1, "asym") for b, cd in itertools.product([8, 4, 2], [torch.int8, torch.int16, torch.int32, torch.int64])]
+    combos += [(4, torch.int32, 0, "asym"), (4, torch.int16, 0, "sym"), (3, torch.int32, 1, "asym"), (4, torch.int32, 1, "sym"),
+               (8, torch.int8, 1, "sym"), (2, torch.int64, 0, "asym")]
+    for bits, cd, dim, scheme in combos:
+        lin = torch.nn.Linear(96, 24)
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(24, 96, generator=g) * 0.05)
+            lin.bias.copy_(torch.randn(24, generator=g) * 0.01)
+        iw, sc, zp = quant_tensor(lin.weight.detach().clone(), dtype="int", bits=bits, return_int=True, group_size=32, scheme=scheme)
+        m = INCWeightOnlyLinear(96, 24, dtype="int", bits=bits, group_size=32, zp=zp is not None, bias=True,
+                                use_optimum_format=False, compression_dtype=cd, compression_dim=dim, device="cpu")
+        m.pack(iw.clone(), sc.clone(), None if zp is None else zp.clone(), lin.bias)
+        x = torch.randn(3, 96, generator=g)
+        out["rowmajor"].append(dict(bits=bits, compression_dtype=cd, compression_dim=dim, scheme=scheme, int_weight=iw, scale=sc,
+                                    zp=zp, bias=lin.bias.detach().clone(), qweight=m.qweight.clone(), scales=m.scales.clone(),
+                                    qzeros=m.qzeros.clone() if zp is not None else None, recover=m.recover().clone(), x=x,
+                                    y=m(x).clone()))
+    probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
+    for tag, kw in RTN_DTYPE_CASES:
+        m = tiny_llama()
+        m = convert(prepare(m, RTNConfig(**kw)))
+        st = woq_state(m)
+        if "fp8" in kw["dtype"]:   # the cast weights are exactly representable in the fp8 type: store them in it
+            f8 = getattr(torch, kw["dtype"].replace("fp8", "float8"))
+            st = {k: v.to(f8) for k, v in m.state_dict().items() if k.endswith("proj.weight")}
+        with torch.no_grad():
+            out["models"][tag] = dict(kw=kw, state=st, logits=m(probe).logits.clone())
+        print("rtn_dtypes:", tag, len(st))
+    out["probe"] = probe
+    torch.save(out, os.path.join(OUT, "rtn_dtypes.pt"))
+
+
+GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack, "rtn_dtypes": gen_rtn_dtypes}
 
 if __name__ == "__main__":
     load_reference()
@@ -430,3 +503,5 @@ if __name__ == "__main__":
             gen_options_extra()
         if "awq_repack" in which:
             gen_awq_repack()
+        if "rtn_dtypes" in which:
+            gen_rtn_dtypes()

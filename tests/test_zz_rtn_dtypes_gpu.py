@@ -1,0 +1,146 @@
+"""RTN over the reference's dtype matrix (test_rtn.py:269-345) on the B200: nf4 / fp4 / fp4_e2m1 through the float4.cu
+kernels, the fp8 casts, and double quantisation of the scales -- against tensors written by the UNMODIFIED reference on
+the CPU (tests/golden/rtn_dtypes.pt, oracle/gen_golden.py rtn_dtypes).  Table-dtype codes / scales / recovered weights
+and the packed int codes must be bit-exact; the double-quantised scales depend on a device-side mean of all scales
+(summation order), so their mismatch fraction is measured and bounded."""
+import os
+
+import pytest
+import torch
+
+from neural_compressor_b200 import dtypes as D
+from tests.test_api_gpu import DEV, tiny_llama
+from tests.test_options_gpu import fields
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(os.path.join(HERE, "golden", "rtn_dtypes.pt"))
+
+
+@pytest.fixture(scope="module")
+def api():
+    import neural_compressor_b200.quantization as q
+
+    return q
+
+
+def test_f4_quantize_kernel_bit_exact(golden):
+    from neural_compressor_b200 import ops
+
+    for case in golden["quant"]:
+        W = case["W"].to(DEV).contiguous()
+        fake = torch.empty_like(W)
+        r = ops.f4_quantize(W, case["dtype"], case["group_size"], case["quantile"], fake_out=fake)
+        tag = (case["dtype"], W.dtype, tuple(W.shape), case["group_size"], case["quantile"])
+        assert torch.equal(r["codes"].cpu(), case["codes"]), tag
+        assert torch.equal(r["scale"].cpu(), case["scale"]), tag
+        assert torch.equal(torch.nan_to_num(fake.float().cpu(), nan=7.0), torch.nan_to_num(case["fake"].float(), nan=7.0)), tag
+        # in place, like quant_tensor
+        ops.f4_quantize(W, case["dtype"], case["group_size"], case["quantile"], want_codes=False, fake_out=W)
+        assert torch.equal(torch.nan_to_num(W.float().cpu(), nan=7.0), torch.nan_to_num(case["fake"].float(), nan=7.0)), tag
+
+
+def test_pack_rows_and_f4_dequantize_kernels(golden):
+    from neural_compressor_b200 import ops
+    from neural_compressor_b200.algorithms.modules_rowmajor import pack_fields
+
+    for case in golden["quant"]:
+        codes, scale = case["codes"], case["scale"]
+        N, K = codes.shape
+        gs = case["group_size"]
+        g = K if (gs <= 0 or gs > K) else gs
+        qw = ops.pack_rows(codes.to(DEV).contiguous(), 4)
+        assert torch.equal(qw.cpu(), pack_fields(codes, 4, torch.int32))
+        lut = torch.zeros(16)
+        for level, c in zip(D.FLOAT_MAPPING[case["dtype"]], D.INT_MAPPING[case["dtype"]]):
+            lut[c & 0xF] = level
+        want = lut[codes.long() & 0xF] * scale[:, torch.arange(K) // g]
+        got = ops.f4_dequantize(qw, scale.to(DEV).contiguous(), case["dtype"], gs, K)
+        assert torch.equal(got.cpu(), want)
+    # other field widths of the row packer
+    g = torch.Generator().manual_seed(3)
+    for bits in (2, 3, 8):
+        c = torch.randint(-(1 << (bits - 1)), 1 << (bits - 1), (17, 101), generator=g).to(torch.int8)
+        assert torch.equal(ops.pack_rows(c.to(DEV).contiguous(), bits).cpu(), pack_fields(c, bits, torch.int32))
+
+
+def run_rtn(api, golden_e2e, kw):
+    m = tiny_llama(golden_e2e["init_state"]).to(DEV)
+    return api.convert(api.prepare(m, api.RTNConfig(use_layer_wise=False, **kw)))
+
+
+def check_logits(m, golden, case, tol):
+    with torch.no_grad():
+        logits = m(golden["probe"].to(DEV)).logits.float().cpu()
+    ref = case["logits"]
+    assert (logits - ref).abs().max().item() < tol * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("tag", ["rtn_nf4", "rtn_fp4", "rtn_fp4_e2m1_bnb", "rtn_fp4_e2m1", "rtn_nf4_mse"])
+def test_rtn_table_dtypes_bit_exact(api, golden_e2e, golden, tag):
+    from neural_compressor_b200.algorithms.modules_rowmajor import B200RowMajorLinear
+
+    case = golden["models"][tag]
+    m = run_rtn(api, golden_e2e, case["kw"])
+    state = m.state_dict()
+    n = 0
+    for k, ref in case["state"].items():
+        got = state[k]
+        assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
+        assert torch.equal(got.cpu(), ref), k
+        n += 1
+    assert n == 28
+    mod = m.model.layers[0].self_attn.q_proj
+    assert isinstance(mod, B200RowMajorLinear) and mod._kernel_recover_ok()
+    u = mod.unpack()
+    lut = torch.tensor(list(D.nibble_levels(case["kw"]["dtype"])))
+    assert torch.equal(mod.recover().cpu(), (u["int_weight"].cpu() * mod.scales.cpu()[:, torch.arange(mod.in_features)
+                                                                                      // mod.group_size]))
+    assert set(u["int_weight"].cpu().unique().tolist()) <= set(lut.tolist())
+    check_logits(m, golden, case, 1e-3)
+
+
+@pytest.mark.parametrize("tag", ["rtn_fp8_e4m3fn", "rtn_fp8_e5m2"])
+def test_rtn_fp8_cast(api, golden_e2e, golden, tag):
+    case = golden["models"][tag]
+    m = run_rtn(api, golden_e2e, case["kw"])
+    state = m.state_dict()
+    for k, ref in case["state"].items():
+        assert isinstance(m.get_submodule(k.rsplit(".", 1)[0]), torch.nn.Linear)
+        assert torch.equal(state[k].float().cpu(), ref.float()), k
+    check_logits(m, golden, case, 1e-3)
+
+
+@pytest.mark.parametrize("tag", ["rtn_int4_dq_asym", "rtn_int4_dq_sym", "rtn_nf4_dq"])
+def test_rtn_double_quant(api, golden_e2e, golden, tag, parity_log):
+    case = golden["models"][tag]
+    m = run_rtn(api, golden_e2e, case["kw"])
+    state = m.state_dict()
+    worst = 0.0
+    for k, ref in case["state"].items():
+        got = state[k].cpu()
+        assert got.shape == ref.shape and got.dtype == ref.dtype, (k, got.shape, ref.shape, got.dtype, ref.dtype)
+        if k.endswith("qweight") or k.endswith("qzeros"):
+            # codes and zero points are computed with the FIRST-level scale (utility.py:377-434): unaffected, bit-exact
+            assert torch.equal(got, ref), k
+        elif k.endswith("scales"):
+            worst = max(worst, (got.float() != ref.float()).float().mean().item())
+            assert (got.float() - ref.float()).abs().max().item() <= 0.05 * ref.float().abs().max().item(), k
+    parity_log(f"rtn_dtypes/{tag}", dict(scale_mismatch_fraction=worst))
+    assert worst <= 2e-3, worst
+    check_logits(m, golden, case, 2e-2)
+
+
+def test_table_dtype_save_load_roundtrip(api, golden_e2e, golden, tmp_path):
+    case = golden["models"]["rtn_nf4"]
+    m = run_rtn(api, golden_e2e, case["kw"])
+    m.save(str(tmp_path))
+    fresh = tiny_llama(golden_e2e["init_state"])
+    loaded = api.load(str(tmp_path), original_model=fresh, device=DEV)
+    for k, ref in case["state"].items():
+        assert torch.equal(loaded.state_dict()[k].cpu(), ref), k
+    check_logits(loaded, golden, case, 1e-3)
