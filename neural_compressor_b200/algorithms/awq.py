@@ -11,12 +11,14 @@ Orchestration stays in Python as in the reference; the numeric inner loops are k
     final RTN + packing                                              (K4, with the per-layer clip quantile)
 The candidate outputs o_q are dense GEMMs over all cached tokens (cuBLAS through torch).
 
-Absorb layers: the reference derives them from a torch.jit.trace graph walk on the CPU (`GraphTrace`,
-utility.py:728-984).  That host-side graph analysis is not rebuilt here: without an explicit
-`absorb_layer_dict` every Linear of a block is its own (self-absorbing) tuple -- exactly what the reference
-itself falls back to when the trace finds nothing (awq.py:40-95, utility.py:675-687), and what it produces for
-Llama under transformers 5.x (tests/golden/e2e_tiny_llama.pt).  An explicit `absorb_layer_dict` is honoured
-with the reference's semantics (awq.py:96-128).
+Absorb layers: the reference derives them from a torch.jit.trace graph walk (`GraphTrace`, utility.py:728-984).  With
+transformers 5.x that trace fails on Hugging Face models and the reference falls back to "every Linear absorbs itself"
+(awq.py:40-95, utility.py:675-687) -- which is what the committed fixtures (tests/golden/e2e_tiny_llama.pt, written by
+the live reference in this image) contain and what this quantizer does by default.  algorithms/absorb.py evaluates the
+same absorption rules on ONE observed eager forward instead (module hooks + TorchDispatchMode; it agrees with GraphTrace on
+the models the reference can still trace).  It is used when `folding=True` (folding is meaningless without it) or when
+asked for (`absorb_discovery="eager"` / B200WOQ_AWQ_ABSORB=eager); the tuples it yields are processed with the reference's
+semantics (awq.py:40-95).  An explicit `absorb_layer_dict` is honoured as in the reference (awq.py:96-128).
 """
 from __future__ import annotations
 
@@ -101,7 +103,7 @@ class ActAwareWeightQuant:
 
     def __init__(self, model, example_inputs=None, data_type="int", bits=4, group_size=32, scheme="asym",
                  use_full_range=False, weight_config=None, total_block_args=None, total_block_kwargs=None,
-                 absorb_layer_dict=None):
+                 absorb_layer_dict=None, absorb_discovery=None):
         self.model = model
         self.device = current_device()
         self.model.to(self.device)
@@ -113,9 +115,48 @@ class ActAwareWeightQuant:
         self.use_full_range = use_full_range
         self.weight_config = weight_config if weight_config is not None else {}
         self.absorb_layer_dict = absorb_layer_dict or {}
+        import os
+
+        self.absorb_discovery = absorb_discovery or os.environ.get("B200WOQ_AWQ_ABSORB", "off")
+        assert self.absorb_discovery in ("off", "eager"), self.absorb_discovery
 
     # ------------------------------------------------------------------ absorb structure
-    def _absorb_per_block(self):
+    def _is_fp32(self, name):
+        return name in self.weight_config and self.weight_config[name].get("dtype") == "fp32"
+
+    def _discovered_per_block(self, folding):
+        """awq.py:40-95 on the tuples of algorithms/absorb.py: per block, the Linears sharing one absorbing module form
+        a tuple; Linears nothing can absorb become self-absorbing 1-tuples unless `folding` asks for folded scales only."""
+        from .absorb import get_absorb_layers
+
+        absorb_to_layer, no_absorb = get_absorb_layers(self.model, self.example_inputs, supported_layers=["Linear"])
+        skip = {k for k, v in absorb_to_layer.items() if any(self._is_fp32(vv) for vv in v)}
+        skip |= {k for k in no_absorb if self._is_fp32(k)}
+        for k in skip:
+            absorb_to_layer.pop(k, None)
+            if k in no_absorb:
+                no_absorb.remove(k)
+        if skip:
+            logger.info(f"{skip} are skipped when running AWQ optimization")
+        block_absorb, inverse = {}, {}
+        for i in range(self.block_num):
+            block_absorb[i] = []
+            prefix = f"{self.block_prefix}.{i}."
+            for k, v in absorb_to_layer.items():
+                names = tuple(vv for vv in v if prefix in vv)
+                if names:
+                    block_absorb[i].append(names)
+                    inverse[names] = k
+            if not folding:
+                for k in no_absorb:
+                    if prefix in k:
+                        block_absorb[i].append((k,))
+                        inverse[(k,)] = k
+        return block_absorb, inverse
+
+    def _absorb_per_block(self, folding=False):
+        if not self.absorb_layer_dict and (folding or self.absorb_discovery == "eager"):
+            return self._discovered_per_block(folding)
         block_absorb, inverse = {}, {}
         for i in range(self.block_num):
             block_absorb[i] = []
@@ -199,7 +240,8 @@ class ActAwareWeightQuant:
     # ------------------------------------------------------------------ the algorithm
     @torch.no_grad()
     def quantize(self, use_auto_scale=True, use_mse_search=True, folding=False, return_int=False):
-        self.block_absorb_dict, self.absorb_layer_dict_full = self._absorb_per_block()
+        # awq.py:216-225; "for only use_mse_search, folding is useless"
+        self.block_absorb_dict, self.absorb_layer_dict_full = self._absorb_per_block(folding if use_auto_scale else False)
         for i, module_list in self.block_absorb_dict.items():
             logger.info(f"Processing block: {i + 1}/{self.block_num}")
             if len(module_list) == 0:
@@ -326,9 +368,10 @@ class ActAwareWeightQuant:
 class AWQQuantizer(Quantizer):
     """awq.py:548-636."""
 
-    def __init__(self, quant_config=None, absorb_layer_dict=None):
+    def __init__(self, quant_config=None, absorb_layer_dict=None, absorb_discovery=None):
         super().__init__(quant_config if quant_config is not None else {})
         self.absorb_layer_dict = absorb_layer_dict or {}
+        self.absorb_discovery = absorb_discovery
 
     @torch.no_grad()
     def prepare(self, model, *args, **kwargs):
@@ -349,6 +392,7 @@ class AWQQuantizer(Quantizer):
         awq = ActAwareWeightQuant(model, example_inputs=example_inputs, data_type=data_type, bits=bits,
                                   group_size=group_size, scheme=scheme, use_full_range=use_full_range,
                                   weight_config=self.quant_config, total_block_args=total_block_args,
-                                  total_block_kwargs=total_block_kwargs, absorb_layer_dict=self.absorb_layer_dict)
+                                  total_block_kwargs=total_block_kwargs, absorb_layer_dict=self.absorb_layer_dict,
+                                  absorb_discovery=self.absorb_discovery)
         return awq.quantize(use_auto_scale=use_auto_scale, use_mse_search=use_mse_search, folding=folding,
                             return_int=return_int)

@@ -478,7 +478,44 @@ def gen_rtn_dtypes():
     torch.save(out, os.path.join(OUT, "rtn_dtypes.pt"))
 
 
-GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack, "rtn_dtypes": gen_rtn_dtypes}
+def gen_awq_toy():
+    """tests/golden/awq_toy.pt: AWQ with discovered absorb layers on a plain nn.Module transformer (tests/toy_models.py),
+    the kind of model the reference's GraphTrace can still trace: folding=False (discovered tuples + self-absorbing
+    leftovers) and folding=True (folded scales only) -- awq.py:40-95, 364-391."""
+    from neural_compressor.torch.algorithms.weight_only.utility import get_absorb_layers
+    from neural_compressor.torch.quantization import AWQConfig, quantize
+
+    from tests.toy_models import Toy
+
+    torch.manual_seed(5)
+    base = Toy(d=64, n=2, variant=0, vocab=64).eval()
+    init = {k: v.clone() for k, v in base.state_dict().items()}
+    g = torch.Generator().manual_seed(17)
+    ids = [torch.randint(0, 64, (1, 16), generator=g) for _ in range(8)]
+    probe = torch.randint(0, 64, (1, 16), generator=g)
+    out = dict(init_state=init, ids=ids, probe=probe, cases={})
+    absorb, no_absorb = get_absorb_layers(base, ids[0], supported_layers=["Linear"])
+    out["absorb_to_layer"], out["no_absorb_layers"] = absorb, no_absorb
+
+    def run_fn(model):
+        for x in ids:
+            model(x)
+
+    for tag, kw in [("folding_false", dict(folding=False)), ("folding_true", dict(folding=True)),
+                    ("folding_true_sym", dict(folding=True, use_sym=True, group_size=64))]:
+        m = Toy(d=64, n=2, variant=0, vocab=64).eval()
+        m.load_state_dict(init)
+        cfg = AWQConfig(bits=4, group_size=kw.pop("group_size", 32), use_sym=kw.pop("use_sym", False), **kw)
+        m = quantize(m, cfg, run_fn=run_fn, example_inputs=ids[0])
+        with torch.no_grad():
+            st = {k: v.clone() for k, v in m.state_dict().items() if "bf16_to_fp8" not in k}
+            out["cases"][tag] = dict(state=st, logits=m(probe).clone())
+        print("awq_toy:", tag, sorted({k.rsplit(".", 1)[-1] for k in st}), len(st))
+    torch.save(out, os.path.join(OUT, "awq_toy.pt"))
+
+
+GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack, "rtn_dtypes": gen_rtn_dtypes,
+                    "awq_toy": gen_awq_toy}
 
 if __name__ == "__main__":
     load_reference()
@@ -505,3 +542,5 @@ if __name__ == "__main__":
             gen_awq_repack()
         if "rtn_dtypes" in which:
             gen_rtn_dtypes()
+        if "awq_toy" in which:
+            gen_awq_toy()
