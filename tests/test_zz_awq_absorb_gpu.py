@@ -52,7 +52,8 @@ def test_awq_discovered_absorption(golden, tag, parity_log, monkeypatch):
         if k.endswith("qweight"):
             worst_code = max(worst_code, (fields(got[k], 4) != fields(ref, 4)).float().mean().item())
         elif "ln" in k or k.endswith("input_scale"):
-            worst_fold = max(worst_fold, ((got[k].cpu().float() - ref.float()).abs().max() / ref.float().abs().max()).item())
+            den = ref.float().abs().max().clamp_min(1e-12)
+            worst_fold = max(worst_fold, ((got[k].cpu().float() - ref.float()).abs().max() / den).item())
     parity_log(f"awq_toy/{tag}", dict(code=worst_code, folded_rel=worst_fold))
     print(tag, worst_code, worst_fold)
     assert worst_fold <= 1e-3, worst_fold       # same alpha chosen for every tuple, scales equal up to reduction order
