@@ -164,18 +164,71 @@ class EagerTrace(TorchDispatchMode):
         return None
 
 
+    def shared_input_root(self, linear) -> Optional[int]:
+        """Identity of the tensor `linear` reads, looked through pass-through ops, when that tensor comes out of a
+        supported module or an element-wise mul and all of its consumers can take a scale -- the condition under which
+        the reference puts Linears that read the same tensor into one scale-sharing group
+        (`get_absorb_to_layer(..., skip_unsupported_layers=False)`, smooth_quant/utility.py:2225-2246)."""
+        t = self.module_input.get(id(linear))
+        for _ in range(16):
+            if t is None or t in self.mutated:
+                return None
+            op, src = self.producer.get(t, (None, None))
+            if t in self.module_output or op in SCALABLE_FUNCTIONAL_OPS:
+                return t if self._scalable_consumers(t) else None
+            if op not in PASS_THROUGH_OPS:
+                return None
+            t = src
+        return None
+
+
+def _trace_model(model, example_inputs):
+    if example_inputs is None:
+        logger.warning("No example_inputs: absorb layer detection is skipped")
+        return None
+    device = next(model.parameters()).device
+    try:
+        return EagerTrace(model).run(model, move_to_device(example_inputs, device))
+    except Exception as ex:  # pragma: no cover
+        logger.warning(f"Eager trace failed ({type(ex).__name__}: {ex}), absorb layer detection is skipped")
+        return None
+
+
+def get_shared_input_groups(model, example_inputs) -> Dict[str, List[str]]:
+    """{first Linear: [Linears reading the same tensor]} over every Linear of the model, in execution order; a Linear
+    whose input cannot be shared (or an unobservable forward) forms its own group.  SmoothQuant's `insert_mul` mode gives
+    each group ONE smoothing scale computed from the concatenated weights (smooth_quant/utility.py:2122-2156, 2225-2246)."""
+    all_linears = [n for n, m in model.named_modules() if type(m).__name__ == "Linear"]
+    trace = _trace_model(model, example_inputs)
+    if trace is None:
+        return {n: [n] for n in all_linears}
+    groups: Dict[str, List[str]] = {}
+    by_root: Dict[int, str] = {}
+    seen = set()
+    for m in trace.calls:
+        if type(m).__name__ != "Linear" or id(m) in seen:
+            continue
+        seen.add(id(m))
+        name = trace.names[id(m)]
+        root = trace.shared_input_root(m)
+        if root is not None and root in by_root:
+            groups[by_root[root]].append(name)
+        else:
+            groups[name] = [name]
+            if root is not None:
+                by_root[root] = name
+    for n in all_linears:       # modules the forward never reached
+        if not any(n in v for v in groups.values()):
+            groups[n] = [n]
+    return groups
+
+
 def get_absorb_layers(model, example_inputs, supported_layers=("Linear",), folding=False):
     """utility.py:657-688: ({absorbing module: [absorbed Linear, ...]}, [Linear names nothing can absorb]).  When the
     forward cannot be observed every Linear is reported as not absorbable, like the reference after a failed trace."""
     all_linears = [n for n, m in model.named_modules() if type(m).__name__ == "Linear"]
-    if example_inputs is None:
-        logger.warning("No example_inputs: absorb layer detection is skipped")
-        return {}, all_linears
-    device = next(model.parameters()).device
-    try:
-        trace = EagerTrace(model).run(model, move_to_device(example_inputs, device))
-    except Exception as ex:  # pragma: no cover
-        logger.warning(f"Eager trace failed ({type(ex).__name__}: {ex}), absorb layer detection is skipped")
+    trace = _trace_model(model, example_inputs)
+    if trace is None:
         return {}, all_linears
     absorb_to_layer: Dict[str, List[str]] = {}
     no_absorb: List[str] = []

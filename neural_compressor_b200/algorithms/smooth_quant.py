@@ -1,9 +1,13 @@
 """SmoothQuant (BASELINE configs[3]) -- calibration statistics + smoothing on the B200.
 
 Reference: neural_compressor/torch/algorithms/smooth_quant/utility.py (Calibration :840-953, cal_scale :605-626,
-SQLinearWrapper :2559-2662, quant_dequant_w_v1/x_v1 :652-755, WrapperLayer.q_dq_forward :2707-2729).
-PARITY UNPINNED: the reference module hard-imports intel_extension_for_pytorch and its W8A8 GEMM lives in
-IPEX/oneDNN outside the tree; this row follows the source text and the QDQ simulation only.
+TorchSmoothQuant._cal_scales :2122-2156 / _absorb_scales :1994-2061 / _parse_absorb_to_layers :2225-2287 / transform
+:2289-2432, SQLinearWrapper :2559-2662, quant_dequant_w_v1/x_v1 :652-755, WrapperLayer.q_dq_forward :2707-2729).
+PARITY: the smoothing transform (calibration ranges, scale-sharing groups, `cal_scale`, folding into the producer, the
+static activation qparams of `SQLinearWrapper`) and the QDQ simulation are pinned against the live reference run on the
+CPU with intel_extension_for_pytorch stubbed (oracle/ref_loader.py load_smooth_quant_utility, tests/golden/
+sq_transform.pt).  The reference's int8 GEMM itself lives in IPEX/oneDNN outside the tree: the W8A8 kernel
+is checked against the QDQ simulation, not against IPEX.
 
 Per-input-channel min/max calibration (stats.cu), the alpha scale, weight smoothing + int8 quantisation
 (b200woq_sq_smooth_quant_weight) and the static W8A8 forward on the tensor cores (b200woq_w8a8_linear_forward,
@@ -39,8 +43,11 @@ class SQLinear(torch.nn.Module):
     `forward_qdq` evaluates the reference's pure-torch QDQ simulation (`WrapperLayer.q_dq_forward`, :2707-2729) for
     cross-checks; it is not used by the product path."""
 
-    def __init__(self, linear: torch.nn.Linear, smooth_scale, act_min, act_max):
+    def __init__(self, linear: torch.nn.Linear, smooth_scale, act_min, act_max, folded=False):
+        """`folded`: the producer of the activation already carries 1/s (`_absorb_scales`, :1994-2061), so there is no
+        run-time multiply; `input_scale` is still kept -- the calibrated range belongs to the un-smoothed activation."""
         super().__init__()
+        self.folded = bool(folded)
         self.in_features, self.out_features = linear.in_features, linear.out_features
         dev = linear.weight.device
         smooth_scale = smooth_scale.to(dev).float().contiguous()
@@ -60,10 +67,11 @@ class SQLinear(torch.nn.Module):
 
     def forward(self, x):
         return ops.w8a8_linear(x, self.qweight, self.w_scale, self.wsum, self.x_scale, self.x_zp, self.in_features,
-                               input_scale=self.input_scale, bias=None if self.bias is None else self.bias.data)
+                               input_scale=None if self.folded else self.input_scale,
+                               bias=None if self.bias is None else self.bias.data)
 
     def forward_qdq(self, x):
-        xs = x.float() * self.input_scale
+        xs = x.float() if self.folded else x.float() * self.input_scale
         q = torch.round(xs / self.x_scale + self.x_zp).clamp_(0, 255)
         xq = self.x_scale * (q - self.x_zp)
         w = self.qweight[:, :self.in_features].float() * self.w_scale.view(-1, 1)
@@ -71,17 +79,48 @@ class SQLinear(torch.nn.Module):
         return y.to(x.dtype)
 
 
+def absorb_scale(layer: torch.nn.Module, scale: torch.Tensor):
+    """`_absorb_scales` (:1994-2061): multiply the producer's output channels by `scale` (= 1 / smoothing scale)."""
+    name = type(layer).__name__
+    if isinstance(layer, (torch.nn.LayerNorm, torch.nn.BatchNorm2d, torch.nn.GroupNorm, torch.nn.InstanceNorm2d)):
+        layer.weight.data.mul_(scale.to(layer.weight.dtype))
+        if getattr(layer, "bias", None) is not None:
+            layer.bias.data.mul_(scale.to(layer.bias.dtype))
+    elif isinstance(layer, torch.nn.Linear):
+        if layer.bias is not None:
+            layer.bias.data.mul_(scale.to(layer.bias.dtype))
+        layer.weight.data.mul_(scale.view(-1, 1).to(layer.weight.dtype))
+    elif name in ("LlamaRMSNorm", "T5LayerNorm"):
+        layer.weight.data.mul_(scale.to(layer.weight.dtype))
+    else:
+        raise NotImplementedError(f"cannot fold a smoothing scale into {name}")
+
+
 class SmoothQuantQuantizer(Quantizer):
-    def __init__(self, quant_config=None):
+    """Calibrate -> group -> smooth -> static W8A8 modules.
+
+    Grouping (which Linears share one smoothing scale, and whether the scale can be folded away) follows
+    `TorchSmoothQuant._parse_absorb_to_layers`.  The reference finds the structure with its torch.jit tracer, which fails
+    on transformers-5 models -- every Linear then gets its own scale and `folding=True` smooths nothing; that observable
+    behaviour is the default here.  `absorb_discovery="eager"` (B200WOQ_SQ_ABSORB=eager), implied by `folding=True`, uses
+    algorithms/absorb.py instead: Linears reading the same tensor share a scale (insert-mul mode), and with
+    `folding=True` only foldable groups are smoothed and 1/s goes into the producing norm / Linear."""
+
+    def __init__(self, quant_config=None, absorb_discovery=None):
         super().__init__(quant_config)
+        import os
+
+        self.absorb_discovery = absorb_discovery or os.environ.get("B200WOQ_SQ_ABSORB", "off")
+        assert self.absorb_discovery in ("off", "eager"), self.absorb_discovery
 
     def prepare(self, model, example_inputs=None, *args, **kwargs):
-        """Register per-input-channel min/max hooks on every Linear (utility.py:858-883)."""
+        """Register per-input-channel min/max hooks on every Linear (utility.py:858-883, 929-953)."""
         self.device = current_device()
         model.to(self.device)
+        self.example_inputs = example_inputs
         self._stats, self._handles = {}, []
         for name, m in model.named_modules():
-            if isinstance(m, torch.nn.Linear) and "lm_head" not in name:
+            if isinstance(m, torch.nn.Linear):
                 k = m.in_features
                 self._stats[name] = (torch.full((k,), -float("inf"), device=self.device),
                                      torch.full((k,), float("inf"), device=self.device))
@@ -93,19 +132,54 @@ class SmoothQuantQuantizer(Quantizer):
                 self._handles.append(m.register_forward_hook(hook))
         return model
 
+    def _groups(self, model, folding):
+        """-> ({key: [Linear names]}, folded).  key = the absorbing module when folded, else the group's first Linear."""
+        calibrated = [n for n, (mx, _) in self._stats.items() if not torch.isinf(mx).any()]
+        if folding or self.absorb_discovery == "eager":
+            from .absorb import get_absorb_layers, get_shared_input_groups
+
+            if folding:
+                absorb_to_layer, _ = get_absorb_layers(model, self.example_inputs, supported_layers=["Linear"])
+                groups = {k: [n for n in v if n in calibrated] for k, v in absorb_to_layer.items()}
+                return {k: v for k, v in groups.items() if v}, True
+            groups = get_shared_input_groups(model, self.example_inputs)
+            groups = {k: [n for n in v if n in calibrated] for k, v in groups.items()}
+            return {v[0]: v for v in groups.values() if v}, False
+        return {n: [n] for n in calibrated}, False
+
     @torch.no_grad()
     def convert(self, model, *args, **kwargs):
         for h in self._handles:
             h.remove()
-        alpha = float(self.quant_config.alpha) if not isinstance(self.quant_config.alpha, str) else 0.5
-        for name, m in list(model.named_modules()):
-            if name not in self._stats:
-                continue
-            mx, mn = self._stats[name]
+        alpha = self.quant_config.alpha
+        if isinstance(alpha, str):
+            logger.warning("alpha='auto' (the reference's AutoAlpha search) is not built; using 0.5")
+            alpha = 0.5
+        alpha = float(alpha)
+        folding = bool(getattr(self.quant_config, "folding", False))
+        for name, (mx, _mn) in self._stats.items():
             if torch.isinf(mx).any():
                 logger.warning(f"{name} saw no calibration data; left in fp")
-                continue
+        groups, folded = self._groups(model, folding)
+        if folding and not groups:
+            logger.warning("empty absorb_to_layer, smoothquant is ignored")   # utility.py:2367-2369
+        modules = dict(model.named_modules())
+        # all scales come from the un-modified weights (`_cal_scales`, :2122-2156) ...
+        scales = {}
+        for key, names in groups.items():
+            mx, mn = self._stats[names[0]]                # the group shares one input (:2132-2136, 2182)
             in_max_abs = torch.maximum(mx.abs(), mn.abs())
-            s = cal_scale(in_max_abs, [m.weight.data.float()], alpha)
-            set_module(model, name, SQLinear(m, s, mn, mx))
+            scales[key] = cal_scale(in_max_abs, [modules[n].weight.data.float() for n in names], alpha)
+        # ... then every fold goes into the still-fp producers (a producer may itself be a smoothed Linear: fc1 takes
+        # fc2's 1/s on its rows and its own s on its columns) ...
+        if folded:
+            for key, s in scales.items():
+                absorb = 1.0 / s
+                absorb[s == 0] = 0                        # :2150-2151
+                absorb_scale(modules[key], absorb)
+        # ... and only then the weights are smoothed and quantised
+        for key, names in groups.items():
+            mx, mn = self._stats[names[0]]
+            for n in names:
+                set_module(model, n, SQLinear(modules[n], scales[key], mn, mx, folded=folded))
         return model

@@ -514,8 +514,73 @@ def gen_awq_toy():
     torch.save(out, os.path.join(OUT, "awq_toy.pt"))
 
 
+def gen_sq_transform():
+    """tests/golden/sq_transform.pt: the reference's SmoothQuant smoothing transform (smooth_quant/utility.py:
+    Calibration :840-953, cal_scale :605-626, TorchSmoothQuant._cal_scales :2122-2156, _scale_layer_weight :1968-1992,
+    _absorb_scales :1994-2061, SQLinearWrapper :2559-2662) on the CPU with IPEX stubbed (oracle/ref_loader.py), plus the
+    QDQ simulation helpers (quant_dequant_w_v1 :652-690, quant_dequant_x_v1 :726-755) on seeded tensors.  Models: the
+    traceable toy transformer (scale sharing / folding through GraphTrace) and the tiny llama (GraphTrace fails under
+    transformers 5: every Linear gets its own scale, folding finds nothing)."""
+    from oracle.ref_loader import load_smooth_quant_utility
+
+    SQ = load_smooth_quant_utility()
+    from tests.toy_models import Toy
+
+    out = dict(models={}, helpers={})
+    g = torch.Generator().manual_seed(23)
+    w = torch.randn(48, 96, generator=g) * 0.05
+    x = torch.randn(64, 96, generator=g) * 2.0
+    lin = torch.nn.Linear(96, 48, bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(w)
+    mn, mx = x.min(0)[0], x.max(0)[0]
+    s = SQ.cal_scale(torch.max(mn.abs(), mx.abs()), [w], 0.5)
+    out["helpers"] = dict(w=w, x=x, cal_scale=s, cal_scale_a08=SQ.cal_scale(torch.max(mn.abs(), mx.abs()), [w, w * 2], 0.8),
+                          qdq_w=SQ.quant_dequant_w_v1(lin).clone(), qdq_x=SQ.quant_dequant_x_v1(x.clone()).clone(),
+                          qdq_x_minmax=SQ.quant_dequant_x_v1(x.clone(), min_x=torch.tensor(-3.0), max_x=torch.tensor(2.5)).clone())
+
+    def run(tag, build, ids, probe, folding, scale_sharing=True, alpha=0.5):
+        m = build()
+
+        def q_func(model):
+            for t in ids:
+                model(t)
+
+        sq = SQ.TorchSmoothQuant(m, dataloader=None, example_inputs=ids[0], q_func=q_func, scale_sharing=scale_sharing)
+        m = sq.transform(alpha=alpha, folding=folding, calib_iter=len(ids), op_types=[torch.nn.Linear])
+        st = {}
+        for n, mod in m.named_modules():
+            if type(mod).__name__ == "SQLinearWrapper":
+                st[n] = dict(input_scale=mod.input_scale.clone(), scale=mod.scale.clone(), zero_point=mod.zero_point.clone(),
+                             weight=mod.sq_linear.weight.detach().clone())
+        with torch.no_grad():
+            out["models"][tag] = dict(folding=folding, scale_sharing=scale_sharing, alpha=alpha, wrappers=st,
+                                      absorb_to_layer=dict(sq.absorb_to_layer or {}),
+                                      input_mins={k: v.clone() for k, v in sq.input_mins.items()},
+                                      input_maxes={k: v.clone() for k, v in sq.input_maxes.items()},
+                                      state={k: v.clone() for k, v in m.state_dict().items()} if folding else None,
+                                      logits=(m(probe)[0] if isinstance(m(probe), tuple) else getattr(m(probe), "logits", m(probe))).clone())
+        print("sq_transform:", tag, len(st), "wrappers; absorb_to_layer", {k: v for k, v in list((sq.absorb_to_layer or {}).items())[:3]})
+
+    awq = torch.load(os.path.join(OUT, "awq_toy.pt"))
+
+    def toy():
+        m = Toy(d=64, n=2, variant=0, vocab=64).eval()
+        m.load_state_dict(awq["init_state"])
+        return m
+
+    for tag, kw in [("toy_insert_mul", dict(folding=False)), ("toy_insert_mul_noshare", dict(folding=False, scale_sharing=False)),
+                    ("toy_folding", dict(folding=True)), ("toy_insert_mul_a08", dict(folding=False, alpha=0.8))]:
+        run(tag, toy, awq["ids"], awq["probe"], **kw)
+    ids = calib_ids(n=8, t=32)
+    probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
+    run("llama_insert_mul", tiny_llama, ids, probe, folding=False)
+    out["llama_ids"], out["llama_probe"] = ids, probe
+    torch.save(out, os.path.join(OUT, "sq_transform.pt"))
+
+
 GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack, "rtn_dtypes": gen_rtn_dtypes,
-                    "awq_toy": gen_awq_toy}
+                    "awq_toy": gen_awq_toy, "sq_transform": gen_sq_transform}
 
 if __name__ == "__main__":
     load_reference()
@@ -544,3 +609,5 @@ if __name__ == "__main__":
             gen_rtn_dtypes()
         if "awq_toy" in which:
             gen_awq_toy()
+        if "sq_transform" in which:
+            gen_sq_transform()

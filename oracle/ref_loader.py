@@ -70,6 +70,30 @@ def _install_stubs():
         sys.modules["accelerate.utils"] = accu
 
 
+def load_smooth_quant_utility():
+    """The reference's SmoothQuant module (torch/algorithms/smooth_quant/utility.py) with `intel_extension_for_pytorch`
+    and `peft` stubbed: the module hard-imports IPEX, but the smoothing transform itself (`TorchSmoothQuant.transform`:
+    calibration, `cal_scale`, absorb grouping, `SQLinearWrapper` and its static activation qparams, the QDQ simulation
+    helpers) is plain torch and runs on the CPU.  Only IPEX's int8 kernels have no counterpart here."""
+    load_reference()
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            for k, v in attrs.items():
+                setattr(m, k, v)
+            sys.modules[name] = m
+        return sys.modules[name]
+
+    ipex = stub("intel_extension_for_pytorch", __version__="2.5.0")
+    ipex.quantization = stub("intel_extension_for_pytorch.quantization")
+    stub("peft", PeftModel=type("PeftModel", (), {}))
+    import neural_compressor.torch.algorithms.smooth_quant.utility as sq_utility
+
+    return sq_utility
+
+
 def load_reference():
     """Return the imported `neural_compressor` package of the reference (CPU forced)."""
     if reference_available():

@@ -484,8 +484,11 @@ def awq_search_clip_module(weight, bias, inputs, group_size, scheme, full_range=
 
 # ----------------------------------------------------------------------------------------
 # SmoothQuant scale math (smooth_quant/utility.py:605-626 cal_scale, :652-755 qdq simulation)
-# PARITY UNPINNED: the reference module hard-imports intel_extension_for_pytorch and cannot be
-# imported in this image, so these follow the source text only.
+# PINNED (round 2): the reference module hard-imports intel_extension_for_pytorch, but with IPEX stubbed
+# (oracle/ref_loader.py load_smooth_quant_utility) its torch-only parts import and run on the CPU; these functions are
+# checked bit for bit against `cal_scale`, `quant_dequant_w_v1`, `quant_dequant_x_v1` and `SQLinearWrapper`'s static
+# qparams in tests/test_smoothquant_transform_cpu.py (fixtures tests/golden/sq_transform.pt).  What stays unpinned is the
+# int8 GEMM itself: it lives in IPEX/oneDNN, outside the tree.
 # ----------------------------------------------------------------------------------------
 def sq_cal_scale(input_max_abs, weights: List[torch.Tensor], alpha: float):
     """smooth_quant/utility.py:605-626."""
@@ -538,7 +541,8 @@ def sq_w8a8_linear(x, W, smooth, act_min, act_max, bias=None, qparams=None):
     `qparams` = (input_scale, s_x, zp_x) overrides the locally derived activation parameters (a device reciprocal may
     differ from the host's in the last bit; the GEMM check wants identical codes on both sides).
 
-    Returns dict(y, q_w int, s_w [N,1], q_x, s_x, zp_x).  PARITY UNPINNED (IPEX absent)."""
+    Returns dict(y, q_w int, s_w [N,1], q_x, s_x, zp_x).  The quantisation parameters are pinned against the live
+    reference; the integer GEMM of IPEX has no reference here."""
     x, W, smooth = _cpu(x).float(), _cpu(W).float(), _cpu(smooth).float()
     input_scale = 1.0 / smooth
     Ws = W * smooth.view(1, -1)
