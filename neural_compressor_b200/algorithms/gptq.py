@@ -514,7 +514,7 @@ class RAWGPTQuantizer:
             for lname in layers:
                 cfg = self.get_layer_config(self.full_name(lname, block_idx))
                 keys_of_slot.setdefault(bank.layer_to_slot[lname], set()).add(
-                    (float(cfg["percdamp"]), bool(cfg["act_order"])))
+                    (float(cfg["percdamp"]), _order_tag(cfg)))
             for lname, layer in layers.items():
                 cfg = self.get_layer_config(self.full_name(lname, block_idx))
                 if cfg.get("static_groups") and cfg["group_size"] not in (-1, layer.weight.shape[-1]):
@@ -523,16 +523,18 @@ class RAWGPTQuantizer:
                     # export then raises IndexError (utility.py:483-537 indexes scale[:, i]); verified on the live reference
                     raise NotImplementedError("static_groups with group_size < in_features: the reference raises "
                                               "IndexError at export (gptq.py:1339-1341); nothing to be drop-in for")
-                if cfg.get("hybrid_order") or cfg.get("fp8_aware"):
-                    raise NotImplementedError("hybrid_order / fp8_aware are HPU (Gaudi) paths of the reference: out of scope")
+                if cfg.get("fp8_aware"):
+                    raise NotImplementedError("fp8_aware is the reference's W4A8 path for HPU (Gaudi) fp8 matmuls: out of scope")
+                if cfg.get("hybrid_order") and cfg.get("act_order"):
+                    raise AssertionError("Error: hybrid_act_order is not allowed with act_order")   # gptq.py:1204
                 if cfg.get("use_double_quant") and str(cfg.get("double_quant_dtype", "int")) != "int":
                     raise NotImplementedError("double quant of scales: int dtype only")
                 slot = bank.layer_to_slot[lname]
-                key = (slot, float(cfg["percdamp"]), bool(cfg["act_order"]))
+                key = (slot, float(cfg["percdamp"]), _order_tag(cfg))
                 if key in by_slot:
                     continue
                 ent = dict(Hinv=None, dead=None, perm=None, info=None, done=None, shared=world == 1,
-                           owner=owner_of_slot[slot], C=bank.acc[slot].shape[0], act_order=bool(cfg["act_order"]))
+                           owner=owner_of_slot[slot], C=bank.acc[slot].shape[0], act_order=bool(_order_tag(cfg)))
                 if ent["owner"] == rank:
                     with on(len(by_slot)):
                         # finalize is in place: clone only when several configs share one raw accumulator
@@ -541,6 +543,9 @@ class RAWGPTQuantizer:
                         perm = None
                         if cfg["act_order"]:
                             perm = torch.argsort(torch.diag(Hc), descending=True)
+                        elif cfg.get("hybrid_order"):
+                            perm = hybrid_order_perm(torch.diag(Hc), int(cfg["group_size"]))
+                        if perm is not None:
                             Hc = Hc[perm][:, perm].contiguous()
                             dead = dead[perm].contiguous()
                         t1 = time.perf_counter()
@@ -555,7 +560,7 @@ class RAWGPTQuantizer:
             fq_side = side
             for li, (lname, layer) in enumerate(layers.items()):
                 cfg = self.get_layer_config(self.full_name(lname, block_idx))
-                key = (bank.layer_to_slot[lname], float(cfg["percdamp"]), bool(cfg["act_order"]))
+                key = (bank.layer_to_slot[lname], float(cfg["percdamp"]), _order_tag(cfg))
                 ent = by_slot[key]
                 # ---- fasterquant (gptq.py:704-713) ----
                 t1 = time.perf_counter()
@@ -573,7 +578,15 @@ class RAWGPTQuantizer:
                         inv = torch.argsort(perm)
                         r["Q"] = r["Q"][:, inv].contiguous()
                         r["codes"] = r["codes"][:, inv].contiguous()
-                        r["perm"] = perm
+                        if cfg["act_order"]:
+                            r["perm"] = perm
+                        else:
+                            # hybrid_order (gptq.py:1320-1328): the groups were visited in `order`; put their
+                            # parameters back in storage order.  order[j] = group processed j-th = perm[j*g] // g
+                            g = int(cfg["group_size"])
+                            inv_order = torch.argsort(perm[::g] // g)
+                            r["scale"] = r["scale"][:, inv_order].contiguous()
+                            r["zero"] = r["zero"][:, inv_order].contiguous()
                     Q = r.pop("Q")
                     layer.weight.data = (Q.t().contiguous() if _is_conv1d(layer) else Q).to(layer.weight.dtype)
                 results[lname] = r
@@ -629,6 +642,29 @@ class RAWGPTQuantizer:
             block = block.to("cpu")
             blocks[block_idx] = block
         return block
+
+
+def _order_tag(cfg) -> str:
+    """Which column order the layer's column loop runs in: "" (natural), "act" (act_order, gptq.py:1212-1216) or
+    "hybrid:<g>" (hybrid_order, :1203-1209).  Part of the key under which a factorised Hessian is shared."""
+    if cfg.get("act_order"):
+        return "act"
+    if cfg.get("hybrid_order"):
+        return f"hybrid:{int(cfg['group_size'])}"
+    return ""
+
+
+def hybrid_order_perm(diag_h: torch.Tensor, group_size: int) -> torch.Tensor:
+    """gptq.py:1389-1461 (`compute_local_perms` / `compute_global_perm` / `compose_final_perm`): columns are sorted by
+    descending diag(H) INSIDE their group and the groups by their largest diagonal entry -- the salient columns come
+    first like with act_order, but no column leaves its group, so the packed module needs no g_idx."""
+    C = diag_h.numel()
+    if group_size <= 0 or C % group_size:
+        raise NotImplementedError("hybrid_order needs group_size > 0 dividing in_features (the reference drops the tail)")
+    d = diag_h.view(C // group_size, group_size)
+    local = torch.argsort(d, dim=1, descending=True)
+    order = torch.argsort(d.max(dim=1).values, descending=True)
+    return (local[order] + (order * group_size).view(-1, 1)).reshape(-1)
 
 
 class GPTQuantizer(Quantizer):

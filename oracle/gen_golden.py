@@ -579,8 +579,28 @@ def gen_sq_transform():
     torch.save(out, os.path.join(OUT, "sq_transform.pt"))
 
 
+def gen_gptq_hybrid():
+    """tests/golden/gptq_hybrid.pt: `hybrid_order=True` (gptq.py:1203-1209, 1320-1328, 1389-1474): columns sorted by
+    diag(H) inside their group, groups by their largest entry; group parameters put back in storage order afterwards."""
+    from neural_compressor.torch.quantization import GPTQConfig, convert, prepare
+
+    ids = calib_ids()
+    probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
+    out = dict(cases={}, probe=probe)
+    for tag, kw in [("hybrid_sym", dict(bits=4, group_size=32, use_sym=True, block_size=128, hybrid_order=True)),
+                    ("hybrid_asym_g64", dict(bits=4, group_size=64, use_sym=False, block_size=128, hybrid_order=True))]:
+        m = prepare(tiny_llama(), GPTQConfig(model_path="/tmp", **kw))
+        for x in ids:
+            m(x)
+        m = convert(m)
+        with torch.no_grad():
+            out["cases"][tag] = dict(kw=kw, state=woq_state(m), logits=m(probe).logits.clone())
+        print("gptq_hybrid:", tag)
+    torch.save(out, os.path.join(OUT, "gptq_hybrid.pt"))
+
+
 GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack, "rtn_dtypes": gen_rtn_dtypes,
-                    "awq_toy": gen_awq_toy, "sq_transform": gen_sq_transform}
+                    "awq_toy": gen_awq_toy, "sq_transform": gen_sq_transform, "gptq_hybrid": gen_gptq_hybrid}
 
 if __name__ == "__main__":
     load_reference()
@@ -611,3 +631,5 @@ if __name__ == "__main__":
             gen_awq_toy()
         if "sq_transform" in which:
             gen_sq_transform()
+        if "gptq_hybrid" in which:
+            gen_gptq_hybrid()

@@ -1,10 +1,11 @@
 """SmoothQuant W8A8 (BASELINE configs[3]) on the OPT-6.7B layer shapes: q/k/v/out [4096,4096], fc1 [16384,4096],
 fc2 [4096,16384]; decode batches M = 1..64 and a 2048-token prefill.
 
-PARITY UNPINNED (IPEX absent): the reference's `smooth_quant` module hard-imports intel_extension_for_pytorch and its
-INT8 GEMM lives in IPEX/oneDNN outside the reference tree, so the checker is the oracle's restatement of
-the reference's own pure-torch W8A8 QDQ simulation (`oracle.sq_w8a8_linear`; smooth_quant/utility.py:652-755,
-2559-2662, 2707-2729).  Integer parts (weight codes, row sums) must be bit-exact; the output is compared with the
+INT8 GEMM PARITY UNPINNED (IPEX absent): the reference's INT8 GEMM lives in IPEX/oneDNN outside the reference tree (SURVEY
+§8c), so the checker is the oracle's restatement of the reference's own pure-torch W8A8 QDQ simulation
+(`oracle.sq_w8a8_linear`; smooth_quant/utility.py:652-755, 2559-2662, 2707-2729) -- whose quantisation parameters and
+helper functions ARE pinned against the live reference (tests/test_smoothquant_transform_cpu.py: `cal_scale`,
+`quant_dequant_w_v1/x_v1`, `SQLinearWrapper._calculate_qparams`, `TorchSmoothQuant.transform` with IPEX stubbed).  Integer parts (weight codes, row sums) must be bit-exact; the output is compared with the
 simulation (fp32 summation order differs: 1e-3) and, on a sample of rows, with exact integer arithmetic in fp64 (1e-5)."""
 import pytest
 import torch
