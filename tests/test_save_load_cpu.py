@@ -99,3 +99,70 @@ def test_awq_repack_matches_reference_fixture():
     qw, qz, sc = repack_awq_to_optimum_format(g["awq_qweight"], g["awq_qzeros"], g["awq_scales"], 4, g["group_size"])
     assert torch.equal(qw, g["qweight"]) and torch.equal(qz, g["qzeros"]) and torch.equal(sc, g["scales"])
     assert qw.dtype == torch.int32 and tuple(qw.shape) == (g["awq_qweight"].shape[0] // 8, g["awq_qweight"].shape[1] * 8)
+
+
+def _optimum_to_autoawq(qweight, qzeros):
+    """Test-side inverse of the repack, written independently: optimum tensors -> AutoAWQ GEMM layout (packed along the
+    output channels, nibble i of a word = column 8*w + [0, 2, 4, 6, 1, 3, 5, 7][i], zero points stored as they are)."""
+    import torch
+
+    def unpack(words, axis):
+        w = words.to(torch.int64) & 0xFFFFFFFF
+        f = torch.stack([(w >> (4 * e)) & 0xF for e in range(8)], dim=axis + 1)
+        shape = list(words.shape)
+        shape[axis] *= 8
+        return f.reshape(shape)
+
+    codes = unpack(qweight, 0)                       # [K, N]
+    zeros = (unpack(qzeros, 1) + 1) & 0xF            # [G, N]   (optimum stores zp - 1)
+    order = [0, 2, 4, 6, 1, 3, 5, 7]
+
+    def pack_awq(v):                                 # [R, N] -> [R, N/8]
+        v = v.reshape(v.shape[0], -1, 8)[:, :, order]
+        w = sum(v[:, :, i] << (4 * i) for i in range(8))
+        return torch.where(w >= 2**31, w - 2**32, w).to(torch.int32)
+
+    return pack_awq(codes), pack_awq(zeros)
+
+
+def test_autoawq_checkpoint_loads_through_the_huggingface_loader(tmp_path):
+    """f1: a checkpoint in AutoAWQ's GEMM layout is repacked to the optimum format at load time, as the reference does
+    (transformers/quantization/utils.py:702 -> utility.py:1432-1459).  The AutoAWQ tensors are derived here from the
+    packed RTN model of the live reference (tests/golden/e2e_tiny_llama.pt) with an independently written inverse, so the
+    loaded modules must hold exactly the reference's optimum tensors.  Loading touches no kernel: it runs on the host."""
+    import json
+    import os
+
+    import torch
+    from safetensors.torch import save_file
+
+    from neural_compressor_b200.algorithms.modules import B200WeightOnlyLinear
+    from neural_compressor_b200.quantization import load
+    from tests.test_api_gpu import tiny_llama
+
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "e2e_tiny_llama.pt"))
+    packed = g["rtn_asym"]["state"]
+    m = tiny_llama(g["init_state"])
+    m.save_pretrained(tmp_path, safe_serialization=True)
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    for k in [k for k in packed if k.endswith(".qweight")]:
+        base = k[: -len(".qweight")]
+        state.pop(base + ".weight")
+        aw, az = _optimum_to_autoawq(packed[base + ".qweight"], packed[base + ".qzeros"])
+        assert tuple(aw.shape) == (packed[base + ".qweight"].shape[0] * 8, packed[base + ".qweight"].shape[1] // 8)
+        state[base + ".qweight"], state[base + ".qzeros"], state[base + ".scales"] = aw, az, packed[base + ".scales"].clone()
+    for fn in os.listdir(tmp_path):
+        if fn.endswith(".safetensors"):
+            os.remove(os.path.join(tmp_path, fn))
+    save_file({k: v.contiguous() for k, v in state.items()}, os.path.join(tmp_path, "model.safetensors"))
+    cfg_file = os.path.join(tmp_path, "config.json")
+    cfg = json.load(open(cfg_file))
+    cfg["quantization_config"] = {"quant_method": "awq", "bits": 4, "group_size": 32, "zero_point": True, "version": "gemm"}
+    json.dump(cfg, open(cfg_file, "w"))
+    loaded = load(str(tmp_path), format="huggingface", device="cpu")
+    sd = loaded.state_dict()
+    n = 0
+    for k, ref in packed.items():
+        assert torch.equal(sd[k], ref), k
+        n += 1
+    assert n == 42 and isinstance(loaded.model.layers[0].self_attn.q_proj, B200WeightOnlyLinear)
