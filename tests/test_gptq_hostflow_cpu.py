@@ -64,6 +64,11 @@ def host_ops(monkeypatch):
         _, qzeros, scales16 = O.pack_optimum(torch.zeros(scale.shape[0], 1), scale, zp, bits, 1)
         return scales16, qzeros
 
+    def dequantize(qweight, qzeros, scales, bits, group_size, in_features, out_features, g_idx=None):
+        # true_sequential runs the later sub-layers on top of already packed ones: recover() + dense GEMM
+        return O.recover_fp16(qweight, qzeros, scales, bits, group_size, in_features, out_features, g_idx)
+
+    monkeypatch.setattr(ops, "dequantize", dequantize)
     for name, fn in dict(hessian_accumulate=hessian_accumulate, hessian_finalize=hessian_finalize,
                          cholesky_inverse_upper=cholesky_inverse_upper, gptq_fasterquant=gptq_fasterquant,
                          pack_codes=pack_codes, pack_params=pack_params).items():
@@ -116,7 +121,17 @@ def test_hybrid_order_host_flow(host_ops, golden_e2e, tag):
     assert m.model.layers[0].self_attn.q_proj.g_idx is None      # no column leaves its group: no g_idx (gptq.py:1203-1209)
 
 
-@pytest.mark.parametrize("tag", ["gptq_act_order", "gptq_b3", "gptq_perchannel"])
+@pytest.mark.parametrize("tag,kw", [("gptq", dict(use_sym=True, block_size=128)), ("gptq_asym", dict(use_sym=False, block_size=128)),
+                                    ("gptq_bs2048", dict(use_sym=True))])
+def test_e2e_cases_host_flow(host_ops, golden_e2e, tag, kw):
+    """The three end-to-end GPTQ fixtures (incl. block_size 2048 > in_features: the whole layer is one lazy block and
+    find_params reads the stale global W)."""
+    m = run_gptq(golden_e2e, dict(bits=4, group_size=32, **kw))
+    compare(m, golden_e2e[tag]["state"])
+
+
+@pytest.mark.parametrize("tag", ["gptq_act_order", "gptq_b3", "gptq_perchannel", "gptq_b8", "gptq_mse_search",
+                                 "gptq_true_sequential"])
 def test_option_cases_host_flow(host_ops, golden_e2e, golden_options, tag):
     case = golden_options["cases"][tag]
     m = run_gptq(golden_e2e, case["kw"])
