@@ -182,13 +182,29 @@ class EagerTrace(TorchDispatchMode):
         return None
 
 
+def _shrink(example_inputs, max_tokens=16):
+    """The trace keeps every tensor of the observed forward alive (identity must stay unique), and the structure does
+    not depend on the sequence length: [batch, seq] tensors (input_ids, attention_mask, ...) are cut to one sample of at
+    most `max_tokens` tokens so that tracing a 70B model does not hold a full-length forward's activations."""
+    def cut(t):
+        if isinstance(t, torch.Tensor) and t.dim() == 2 and (t.shape[0] > 1 or t.shape[1] > max_tokens):
+            return t[:1, :max_tokens]
+        return t
+
+    if isinstance(example_inputs, dict):
+        return {k: cut(v) for k, v in example_inputs.items()}
+    if isinstance(example_inputs, (list, tuple)):
+        return type(example_inputs)(cut(v) for v in example_inputs)
+    return cut(example_inputs)
+
+
 def _trace_model(model, example_inputs):
     if example_inputs is None:
         logger.warning("No example_inputs: absorb layer detection is skipped")
         return None
     device = next(model.parameters()).device
     try:
-        return EagerTrace(model).run(model, move_to_device(example_inputs, device))
+        return EagerTrace(model).run(model, move_to_device(_shrink(example_inputs), device))
     except Exception as ex:  # pragma: no cover
         logger.warning(f"Eager trace failed ({type(ex).__name__}: {ex}), absorb layer detection is skipped")
         return None
