@@ -8,8 +8,11 @@ defaults so user scripts keep working unchanged:
     BaseConfig         neural_compressor/common/base_config.py:190- (set_local :297-316, to_config_mapping
                        :586-617, to_dict/from_dict :350-425)
 
-Only the mechanics the hot path needs are implemented (global + local configs, regex / type matching,
-dict round trip); the tuning-grid expansion of list-valued parameters is out of scope.
+Implemented: global + local configs, regex / module-type / white-list matching, dict and json round trips, `+`
+(same class: merge of the local entries; different classes: `ComposableConfig`), multi-algorithm dict configs -- the
+operations of the reference's test/torch/test_config.py, checked side by side with the live reference in
+tests/test_config_cpu.py.  The tuning-grid expansion of list-valued parameters (`expand`, autotune) is out of scope
+(SURVEY §2.1 row 7).
 """
 from __future__ import annotations
 
@@ -81,8 +84,7 @@ class BaseConfig:
         if self._local_config:
             result["local"] = {}
             for op, cfg in self._local_config.items():
-                key = op if isinstance(op, str) else op.__name__
-                result["local"][key] = cfg.to_dict()
+                result["local"][op] = cfg.to_dict()     # a module type stays the key it was given as (base_config.py:326-329)
             if self._global_config is not None:
                 result["global"] = global_config
         else:
@@ -100,6 +102,33 @@ class BaseConfig:
 
     def __repr__(self):
         return f"{self.__class__.__name__}({self.to_dict()})"
+
+    # ---- json (base_config.py:427-452) ----
+    def to_json_string(self, use_diff: bool = False) -> str:
+        import json
+
+        return json.dumps(self.to_dict(), indent=2) + "\n"
+
+    def to_json_file(self, filename):
+        with open(filename, "w", encoding="utf-8") as f:
+            f.write(self.to_json_string())
+
+    @classmethod
+    def from_json_file(cls, filename):
+        import json
+
+        with open(filename, "r", encoding="utf-8") as f:
+            return cls.from_dict(json.load(f))
+
+    # ---- composition (base_config.py:454-471) ----
+    def __add__(self, other: "BaseConfig") -> "BaseConfig":
+        """Same class: the other config's local entries are merged into this one (its global part is dropped).
+        Different classes: a `ComposableConfig` holding both."""
+        if isinstance(other, type(self)):
+            for op_name, config in other.local_config.items():
+                self.set_local(op_name, config)
+            return self
+        return ComposableConfig(configs=[self, other])
 
     # ---- model walk + mapping ----
     @staticmethod
@@ -127,6 +156,79 @@ class BaseConfig:
                     if re.match(pattern, op_name):
                         mapping[(op_name, op_type)] = sub
         return mapping
+
+
+class ComposableConfig(BaseConfig):
+    """Several algorithms' configs applied to one model, built with `+` or from a multi-key dict
+    (base_config.py:684-830).  The mapping takes, per member config, the entries its own `to_config_mapping` yields for
+    the modules that member's `get_model_info` reports (the reference's composable mapping applies the LOCAL entries only,
+    :794-816; the per-algorithm entry functions then pick the operators carrying their own config class)."""
+
+    name = "composable_config"
+
+    def __init__(self, configs):
+        self.config_list = list(configs)
+
+    def __add__(self, other):
+        if isinstance(other, ComposableConfig):
+            self.config_list.extend(other.config_list)
+        else:
+            self.config_list.append(other)
+        return self
+
+    def to_dict(self):
+        return {config.name: config.to_dict() for config in self.config_list}
+
+    @classmethod
+    def from_dict(cls, config_dict, config_registry=None):
+        registry = config_registry or {c.name: c for c in (RTNConfig, GPTQConfig, AWQConfig, SmoothQuantConfig)}
+        assert len(config_dict) >= 1, "The config dict must include at least one configuration."
+        config = None
+        for name, value in config_dict.items():
+            part = registry[name].from_dict(value)
+            config = part if config is None else config + part
+        return config
+
+    def to_json_string(self, use_diff: bool = False) -> str:
+        import json
+
+        return json.dumps(self.to_dict(), indent=2) + "\n"
+
+    def __repr__(self):
+        return f"{self.__class__.__name__} {self.to_json_string()}"
+
+    def get_model_info(self, model, *args, **kwargs):
+        return {config.name: config.get_model_info(model, *args, **kwargs) for config in self.config_list}
+
+    def to_config_mapping(self, config_list=None, model_info=None):
+        mapping = OrderedDict()
+        for config in self.config_list:
+            info = model_info.get(config.name) if isinstance(model_info, dict) else model_info
+            by_type, by_name = {}, {}
+            for key, sub in config.local_config.items():
+                if isinstance(key, str) and not _looks_like_type_name(key):
+                    by_name[key] = sub
+                else:
+                    by_type[key if isinstance(key, str) else key.__name__] = sub
+            for op_name, op_type in info:
+                if op_type in by_type:
+                    mapping[(op_name, op_type)] = by_type[op_type]
+                for pattern, sub in by_name.items():
+                    if re.match(pattern, op_name):
+                        mapping[(op_name, op_type)] = sub
+        return mapping
+
+
+def get_model_info(model: torch.nn.Module, white_module_list=None) -> List[Tuple[str, str]]:
+    """torch/utils/utility.py `get_model_info`: (name, type name) of every module of the listed types, first occurrence
+    only (a module object reachable under two names is reported once)."""
+    white = tuple(white_module_list) if white_module_list is not None else _woq_white_list()
+    seen, out = set(), []
+    for name, module in model.named_modules():
+        if isinstance(module, white) and (name, type(module).__name__) not in seen:
+            seen.add((name, type(module).__name__))
+            out.append((name, type(module).__name__))
+    return out
 
 
 def _looks_like_type_name(key: str) -> bool:

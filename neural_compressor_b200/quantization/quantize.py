@@ -6,7 +6,7 @@ from typing import Any, Callable
 import torch
 
 from ..utils import Mode, algos_mapping, logger
-from .config import AWQConfig, BaseConfig, GPTQConfig, RTNConfig, SmoothQuantConfig
+from .config import AWQConfig, BaseConfig, ComposableConfig, GPTQConfig, RTNConfig, SmoothQuantConfig
 
 _CONFIG_BY_NAME = {c.name: c for c in (RTNConfig, GPTQConfig, AWQConfig, SmoothQuantConfig)}
 
@@ -17,9 +17,8 @@ def need_apply(configs_mapping, algo_name):
 
 def _as_config(quant_config):
     if isinstance(quant_config, dict):
-        # {"rtn": {...}} as produced by ComposableConfig.to_dict(); single-algorithm dicts only
-        (name, body), = quant_config.items()
-        return _CONFIG_BY_NAME[name].from_dict(body)
+        # {"rtn": {...}[, "gptq": {...}]} as produced by (Composable)Config.to_dict()   (quantize.py:81-84)
+        return ComposableConfig.from_dict(quant_config, config_registry=_CONFIG_BY_NAME)
     assert isinstance(quant_config, BaseConfig), (
         f"Please pass a dict or config instance as the quantization configuration, but got {type(quant_config)}.")
     return quant_config
