@@ -121,7 +121,9 @@ class RTNQuantizer(Quantizer):
             is_conv1d = bool(conv1d) and isinstance(m, conv1d)
             transpose = (group_dim == 0) ^ is_conv1d   # rtn.py:209-216
             if group_dim == 0 and not is_conv1d:
-                raise NotImplementedError("group_dim=0 on nn.Linear has no packed B200 layout")
+                # the reference cannot run this either: its scales come out as [N/g, K] and INCWeightOnlyLinear.pack
+                # asserts on the shape (modules.py:345; verified on the live reference for square and non-square layers)
+                raise AssertionError("group_dim=0 on nn.Linear: Scale shape is mismatched.")
             w = m.weight.detach().to(device)
             w = w.t().contiguous() if transpose else w.contiguous()   # [N = out, K = in]
             if use_mse_search:

@@ -86,3 +86,12 @@ def test_double_quant_skipped_for_ragged_k(host_ops):
     a = api.convert(api.prepare(lin, api.RTNConfig(group_size=32, use_double_quant=True, use_layer_wise=False)))
     b = api.convert(api.prepare(ref, api.RTNConfig(group_size=32, use_layer_wise=False)))
     assert torch.equal(a[0].scales, b[0].scales) and torch.equal(a[0].qweight, b[0].qweight)
+
+
+def test_group_dim0_on_linear_fails_like_the_reference(host_ops):
+    """`RTNConfig(group_dim=0)` on an nn.Linear dies in the reference with "Scale shape is mismatched" (modules.py:345)."""
+    import neural_compressor_b200.quantization as api
+
+    m = torch.nn.Sequential(torch.nn.Linear(64, 32))
+    with pytest.raises(AssertionError, match="Scale shape is mismatched"):
+        api.convert(api.prepare(m, api.RTNConfig(group_dim=0, group_size=32, use_layer_wise=False)))
