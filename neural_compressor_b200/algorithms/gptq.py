@@ -368,6 +368,7 @@ class RAWGPTQuantizer:
         if _dist_rank() == owner:
             if cur is not None and ent["done"] is not None:
                 cur.wait_event(ent["done"])
+            ent["Hinv"] = ent["Hinv"].contiguous()   # a collective ships storage order (no-op for the kernel's output)
         else:
             ent["Hinv"] = torch.empty((C, C), dtype=torch.float32, device=self.device)
             ent["dead"] = torch.empty(C, dtype=torch.uint8, device=self.device)

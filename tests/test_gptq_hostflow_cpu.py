@@ -13,69 +13,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.fixture()
 def host_ops(monkeypatch):
-    import math
+    from tests.host_twins import install_gptq_twins
 
-    from neural_compressor_b200 import ops
-    from neural_compressor_b200.algorithms import gptq as G
-    from oracle import woq_oracle as O
-
-    running = {}   # id(raw accumulator) -> [H running mean, nsamples]   (gptq.py:1111-1141)
-
-    def hessian_accumulate(X, Hsum):
-        st = running.setdefault(id(Hsum), [torch.zeros_like(Hsum), 0, Hsum])
-        x = X.unsqueeze(0) if X.dim() == 2 else X
-        b = x.shape[0]
-        x2 = x.reshape(-1, x.shape[-1]).t().float()
-        st[0] *= st[1] / (st[1] + b)
-        st[1] += b
-        x2 = math.sqrt(2 / st[1]) * x2
-        st[0] += x2.matmul(x2.t())
-
-    def hessian_finalize(Hsum, nsamples, percdamp):
-        H = running[id(Hsum)][0].clone()
-        dead = torch.diag(H) == 0
-        H[dead, dead] = 1
-        H[torch.arange(H.shape[0]), torch.arange(H.shape[0])] += percdamp * torch.mean(torch.diag(H))
-        return H, dead.to(torch.uint8)
-
-    def cholesky_inverse_upper(H, info=None, check=True):
-        if info is not None:
-            info.zero_()
-        return O.GPTQLayerOracle.cholesky_inverse_upper(H)
-
-    def gptq_fasterquant(W, Hinv, dead_mask, blocksize=128, groupsize=-1, bits=4, sym=False, mse=False, want_q=True,
-                         double_quant=None):
-        assert double_quant is None
-        N, C = W.shape
-        W = W.clone()
-        if dead_mask is not None:
-            W[:, dead_mask.bool()] = 0
-        r = O.GPTQLayerOracle(N, C, bits=bits, sym=sym, mse=mse).fasterquant(W, blocksize=blocksize, groupsize=groupsize, hinv=Hinv)
-        g = C if groupsize <= 0 else groupsize
-        idx = torch.arange(C) // g
-        codes = torch.clamp(torch.round(r["Q"] / r["scale"][:, idx]) + r["zero"][:, idx], 0, 2**bits - 1).to(torch.uint8)
-        return dict(codes=codes, Q=r["Q"] if want_q else None, scale=r["scale"], zero=r["zero"], losses=r["losses"].sum(1))
-
-    def pack_codes(codes, bits):
-        q, _, _ = O.pack_optimum(codes.float(), torch.ones(codes.shape[0], 1), torch.zeros(codes.shape[0], 1), bits, codes.shape[1])
-        return q
-
-    def pack_params(scale, zp, bits):
-        _, qzeros, scales16 = O.pack_optimum(torch.zeros(scale.shape[0], 1), scale, zp, bits, 1)
-        return scales16, qzeros
-
-    def dequantize(qweight, qzeros, scales, bits, group_size, in_features, out_features, g_idx=None):
-        # true_sequential runs the later sub-layers on top of already packed ones: recover() + dense GEMM
-        return O.recover_fp16(qweight, qzeros, scales, bits, group_size, in_features, out_features, g_idx)
-
-    monkeypatch.setattr(ops, "dequantize", dequantize)
-    for name, fn in dict(hessian_accumulate=hessian_accumulate, hessian_finalize=hessian_finalize,
-                         cholesky_inverse_upper=cholesky_inverse_upper, gptq_fasterquant=gptq_fasterquant,
-                         pack_codes=pack_codes, pack_params=pack_params).items():
-        monkeypatch.setattr(ops, name, fn)
-    monkeypatch.setattr(G, "current_device", lambda: torch.device("cpu"), raising=False)
+    install_gptq_twins(running_mean=True, setter=monkeypatch.setattr)
     monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
-    return ops
 
 
 def run_gptq(golden_e2e, kw):
