@@ -691,7 +691,10 @@ class GPTQuantizer(Quantizer):
         self.gptq_quantizer.model = model
         self.gptq_quantizer.remove_prepare_for_calibration()
         q_model = self.gptq_quantizer.execute_quantization()
-        # packed modules live on the B200; keep the rest of the model with them
-        q_model = q_model.to(self.gptq_quantizer.device)
+        # packed modules live on the B200; keep the rest of the model with them.  A layer-sharded model (utils/sharded.py)
+        # was built on the device already and its remote blocks are storage-less skeletons that cannot be moved
+        shard = getattr(q_model, "_b200_shard", None)
+        if shard is None or shard["world"] == 1:
+            q_model = q_model.to(self.gptq_quantizer.device)
         logger.info("GPTQ quantizing done.")
         return q_model

@@ -194,7 +194,7 @@ def test_layer_sharded_model_fetch_release_gloo_world2():
     assert dict(ret) == {0: True, 1: True}
 
 
-def _engine_worker(rank, world, port, ret, golden_path):
+def _engine_worker(rank, world, port, ret, golden_path, layer_sharded=False):
     """The WHOLE GPTQ engine at world size 2 on the CPU (kernels = oracle twins, tests/host_twins.py): each rank calibrates
     on its half of the sequences; raw Hessians are reduced to their owners, owners factorise and broadcast, every column
     loop runs row-sharded and exchanges u8 codes + parameters."""
@@ -208,12 +208,30 @@ def _engine_worker(rank, world, port, ret, golden_path):
 
     install_gptq_twins(running_mean=False)
     g = torch.load(golden_path)
-    m = tiny_llama(g["init_state"])
+    if layer_sharded:
+        # BASELINE configs[4] in miniature: rank r holds block r only (the other one is a meta skeleton), the owner
+        # broadcasts a block right before it is processed, the packed block stays with its owner
+        from neural_compressor_b200.utils import sharded
+
+        def init(mod, idx):
+            for n, p in mod.named_parameters():
+                p.data.copy_(g["init_state"][f"{mod._b200_path}.{n}"])
+
+        m = sharded.build_layer_sharded(lambda: tiny_llama(g["init_state"]) if False else _empty_tiny_llama(), "model.layers",
+                                        rank, world, "cpu", init=init)
+        m.eval()
+        m.config.use_cache = False
+    else:
+        m = tiny_llama(g["init_state"])
     m = api.prepare(m, api.GPTQConfig(bits=4, group_size=32, use_sym=True, block_size=128))
     for x in g["ids"][rank::world]:
         m(x)
     m = api.convert(m)
-    state = {k: v for k, v in m.state_dict().items() if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales")}
+    state = {k: v for k, v in m.state_dict().items() if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales") and not v.is_meta}
+    if layer_sharded:
+        ret[rank] = dict(same=all(f".layers.{rank}." in k for k in state) and len(state) == 21, state=state)
+        dist.destroy_process_group()
+        return
     same = True
     for k in sorted(state):          # every rank must end with the identical packed model
         t = state[k].to(torch.float32) if state[k].dtype == torch.float16 else state[k]
@@ -224,7 +242,16 @@ def _engine_worker(rank, world, port, ret, golden_path):
     dist.destroy_process_group()
 
 
-def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch):
+def _empty_tiny_llama():
+    from transformers import LlamaConfig, LlamaForCausalLM
+
+    return LlamaForCausalLM(LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                                        num_key_value_heads=4, vocab_size=512, max_position_embeddings=128,
+                                        tie_word_embeddings=False))
+
+
+@pytest.mark.parametrize("layer_sharded", [False, True])
+def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch, layer_sharded):
     from tests.host_twins import install_gptq_twins
     from tests.test_api_gpu import tiny_llama
     from tests.test_options_gpu import fields
@@ -234,7 +261,7 @@ def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch):
     mgr = mp.Manager()
     ret = mgr.dict()
     port = 29312 + os.getpid() % 200
-    mp.spawn(_engine_worker, args=(world, port, ret, golden_path), nprocs=world, join=True)
+    mp.spawn(_engine_worker, args=(world, port + int(layer_sharded), ret, golden_path, layer_sharded), nprocs=world, join=True)
     assert ret[0]["same"] and ret[1]["same"]
     # single process, same twins, all 16 sequences
     import neural_compressor_b200.quantization as api
@@ -246,7 +273,9 @@ def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch):
     for x in g["ids"]:
         m(x)
     single = api.convert(m).state_dict()
-    multi = ret[0]["state"]
+    multi = dict(ret[0]["state"])
+    if layer_sharded:
+        multi.update(ret[1]["state"])        # each rank keeps the packed blocks it owns
     assert len(multi) == 42
     worst, differing, worst_scale = 0.0, 0, 0.0
     for k, v in multi.items():
