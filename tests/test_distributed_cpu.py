@@ -194,7 +194,7 @@ def test_layer_sharded_model_fetch_release_gloo_world2():
     assert dict(ret) == {0: True, 1: True}
 
 
-def _engine_worker(rank, world, port, ret, golden_path, layer_sharded=False):
+def _engine_worker(rank, world, port, ret, golden_path, layer_sharded=False, extra=None):
     """The WHOLE GPTQ engine at world size 2 on the CPU (kernels = oracle twins, tests/host_twins.py): each rank calibrates
     on its half of the sequences; raw Hessians are reduced to their owners, owners factorise and broadcast, every column
     loop runs row-sharded and exchanges u8 codes + parameters."""
@@ -223,11 +223,12 @@ def _engine_worker(rank, world, port, ret, golden_path, layer_sharded=False):
         m.config.use_cache = False
     else:
         m = tiny_llama(g["init_state"])
-    m = api.prepare(m, api.GPTQConfig(bits=4, group_size=32, use_sym=True, block_size=128))
+    m = api.prepare(m, api.GPTQConfig(bits=4, group_size=32, use_sym=True, block_size=128, **(extra or {})))
     for x in g["ids"][rank::world]:
         m(x)
     m = api.convert(m)
-    state = {k: v for k, v in m.state_dict().items() if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales") and not v.is_meta}
+    state = {k: v for k, v in m.state_dict().items()
+             if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales", "g_idx") and not v.is_meta}
     if layer_sharded:
         ret[rank] = dict(same=all(f".layers.{rank}." in k for k in state) and len(state) == 21, state=state)
         dist.destroy_process_group()
@@ -250,8 +251,9 @@ def _empty_tiny_llama():
                                         tie_word_embeddings=False))
 
 
-@pytest.mark.parametrize("layer_sharded", [False, True])
-def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch, layer_sharded):
+@pytest.mark.parametrize("layer_sharded,extra", [(False, None), (True, None), (False, dict(hybrid_order=True)),
+                                                 (False, dict(act_order=True))])
+def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch, layer_sharded, extra):
     from tests.host_twins import install_gptq_twins
     from tests.test_api_gpu import tiny_llama
     from tests.test_options_gpu import fields
@@ -261,7 +263,8 @@ def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch, layer_
     mgr = mp.Manager()
     ret = mgr.dict()
     port = 29312 + os.getpid() % 200
-    mp.spawn(_engine_worker, args=(world, port + int(layer_sharded), ret, golden_path, layer_sharded), nprocs=world, join=True)
+    port += int(layer_sharded) + (2 if extra else 0) + (1 if extra and "act_order" in extra else 0)
+    mp.spawn(_engine_worker, args=(world, port, ret, golden_path, layer_sharded, extra), nprocs=world, join=True)
     assert ret[0]["same"] and ret[1]["same"]
     # single process, same twins, all 16 sequences
     import neural_compressor_b200.quantization as api
@@ -269,17 +272,19 @@ def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch, layer_
     install_gptq_twins(running_mean=False, setter=monkeypatch.setattr)
     monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
     g = torch.load(golden_path)
-    m = api.prepare(tiny_llama(g["init_state"]), api.GPTQConfig(bits=4, group_size=32, use_sym=True, block_size=128))
+    m = api.prepare(tiny_llama(g["init_state"]), api.GPTQConfig(bits=4, group_size=32, use_sym=True, block_size=128, **(extra or {})))
     for x in g["ids"]:
         m(x)
     single = api.convert(m).state_dict()
     multi = dict(ret[0]["state"])
     if layer_sharded:
         multi.update(ret[1]["state"])        # each rank keeps the packed blocks it owns
-    assert len(multi) == 42
+    assert len(multi) == (56 if extra and "act_order" in extra else 42)
     worst, differing, worst_scale = 0.0, 0, 0.0
     for k, v in multi.items():
-        if k.endswith("scales"):
+        if k.endswith("g_idx"):
+            assert torch.equal(v, single[k]), k          # the broadcast permutation is the owner's, bit for bit
+        elif k.endswith("scales"):
             worst_scale = max(worst_scale, ((v.float() - single[k].float()).abs().max() / single[k].float().abs().max()).item())
         else:
             frac = (fields(v, 4) != fields(single[k], 4)).float().mean().item()
