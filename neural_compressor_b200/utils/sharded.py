@@ -10,7 +10,7 @@ the non-owners drop it again -- every GPU is busy in every phase, no GPU ever ho
 """
 from __future__ import annotations
 
-from typing import Callable, List, Optional
+from typing import Callable, Optional
 
 import torch
 
