@@ -599,8 +599,64 @@ def gen_gptq_hybrid():
     torch.save(out, os.path.join(OUT, "gptq_hybrid.pt"))
 
 
+def family_models():
+    """Tiny random-init models of other architectures than Llama: OPT (biased linears, LayerNorm, ReLU MLP), GPT-J
+    (parallel attention / MLP reading one LayerNorm) and GPT-2 (transformers.Conv1D weights stored [in, out])."""
+    from transformers import GPT2Config, GPT2LMHeadModel, GPTJConfig, GPTJForCausalLM, OPTConfig, OPTForCausalLM
+
+    def build(name):
+        torch.manual_seed(0)
+        if name == "opt":
+            m = OPTForCausalLM(OPTConfig(hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4, vocab_size=256,
+                                         max_position_embeddings=128, word_embed_proj_dim=64))
+        elif name == "gptj":
+            m = GPTJForCausalLM(GPTJConfig(n_embd=64, n_layer=2, n_head=4, n_positions=128, vocab_size=256, rotary_dim=8))
+        else:
+            m = GPT2LMHeadModel(GPT2Config(n_embd=64, n_layer=2, n_head=4, vocab_size=256, n_positions=128))
+        m.eval()
+        m.config.use_cache = False
+        return m
+
+    return build
+
+
+def gen_families():
+    """tests/golden/families.pt: GPTQ and AWQ on tiny OPT / GPT-J / GPT-2 models (the reference's own tests run on a tiny
+    GPT-J): calibration capture with each architecture's block signature, biased linears, Conv1D transposes."""
+    from neural_compressor.torch.quantization import AWQConfig, GPTQConfig, convert, prepare, quantize
+
+    build = family_models()
+    ids = calib_ids(n=8, t=32, vocab=256)
+    probe = torch.randint(0, 256, (1, 16), generator=torch.Generator().manual_seed(99))
+    out = dict(ids=ids, probe=probe, init={}, cases={})
+
+    def run_fn(model):
+        for x in ids:
+            model(x)
+
+    for name in ("opt", "gptj", "gpt2"):
+        out["init"][name] = {k: v.clone() for k, v in build(name).state_dict().items()}
+        try:
+            m = prepare(build(name), GPTQConfig(bits=4, group_size=32, use_sym=False, block_size=128, model_path="/tmp"))
+            run_fn(m)
+            m = convert(m)
+            with torch.no_grad():
+                out["cases"][f"gptq_{name}"] = dict(state=woq_state(m), logits=m(probe).logits.clone())
+            print("families: gptq", name, len(out["cases"][f"gptq_{name}"]["state"]))
+        except Exception as ex:   # GPT-2: the reference's own export trips over the Conv1D layout (gptq.py:796-813)
+            out["cases"][f"gptq_{name}"] = dict(reference_error=f"{type(ex).__name__}: {ex}")
+            print("families: gptq", name, "REFERENCE FAILS:", out["cases"][f"gptq_{name}"]["reference_error"][:100])
+        if name != "gpt2":     # AWQ walks nn.Linear modules
+            m = quantize(build(name), AWQConfig(bits=4, group_size=32, use_sym=False), run_fn=run_fn, example_inputs=ids[0])
+            with torch.no_grad():
+                out["cases"][f"awq_{name}"] = dict(state=woq_state(m), logits=m(probe).logits.clone())
+            print("families: awq", name, len(out["cases"][f"awq_{name}"]["state"]))
+    torch.save(out, os.path.join(OUT, "families.pt"))
+
+
 GENERATORS_EXTRA = {"options_extra": gen_options_extra, "awq_repack": gen_awq_repack, "rtn_dtypes": gen_rtn_dtypes,
-                    "awq_toy": gen_awq_toy, "sq_transform": gen_sq_transform, "gptq_hybrid": gen_gptq_hybrid}
+                    "awq_toy": gen_awq_toy, "sq_transform": gen_sq_transform, "gptq_hybrid": gen_gptq_hybrid,
+                    "families": gen_families}
 
 if __name__ == "__main__":
     load_reference()
@@ -633,3 +689,5 @@ if __name__ == "__main__":
             gen_sq_transform()
         if "gptq_hybrid" in which:
             gen_gptq_hybrid()
+        if "families" in which:
+            gen_families()
