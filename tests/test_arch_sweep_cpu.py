@@ -1,0 +1,115 @@
+"""Architecture sweep, side by side with the LIVE reference (skipped where /root/reference is absent): tiny random-init
+Mistral, Qwen2, Falcon, Bloom, GPT-NeoX, Phi, Gemma and MPT models go through the reference's GPTQ / AWQ on the CPU and
+through this package's engines with the kernels swapped for their oracle twins (tests/host_twins.py).  The packed tensors
+must coincide: every architecture brings its own block signature (alibi, position embeddings, parallel attention, fused
+qkv, biased linears) to the calibration capture and the per-input Hessian sharing."""
+import copy
+
+import pytest
+import torch
+
+from tests.test_awq_absorb_cpu import host_ops as awq_host_ops  # noqa: F401  (fixture)
+from tests.test_options_gpu import fields
+
+ARCHS = ["mistral", "qwen2", "falcon", "bloom", "gpt_neox", "phi", "gemma", "mpt"]
+
+
+def build(name):
+    import transformers as T
+
+    torch.manual_seed(0)
+    v = dict(vocab_size=256)
+    llama_like = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, max_position_embeddings=128, **v)
+    if name == "mistral":
+        m = T.MistralForCausalLM(T.MistralConfig(**llama_like))
+    elif name == "qwen2":
+        m = T.Qwen2ForCausalLM(T.Qwen2Config(**llama_like))
+    elif name == "gemma":
+        m = T.GemmaForCausalLM(T.GemmaConfig(head_dim=16, **llama_like))
+    elif name == "falcon":
+        m = T.FalconForCausalLM(T.FalconConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, **v))
+    elif name == "bloom":
+        m = T.BloomForCausalLM(T.BloomConfig(hidden_size=64, n_layer=2, n_head=4, **v))
+    elif name == "gpt_neox":
+        m = T.GPTNeoXForCausalLM(T.GPTNeoXConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                                 num_attention_heads=4, max_position_embeddings=128, **v))
+    elif name == "phi":
+        m = T.PhiForCausalLM(T.PhiConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                                         max_position_embeddings=128, **v))
+    else:
+        m = T.MptForCausalLM(T.MptConfig(d_model=64, n_heads=4, n_layers=2, max_seq_len=128, **v))
+    m.eval()
+    m.config.use_cache = False
+    return m
+
+
+@pytest.fixture(scope="module")
+def ref_api():
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    import neural_compressor.torch.quantization as ref
+
+    return ref
+
+
+@pytest.fixture(scope="module")
+def ids():
+    g = torch.Generator().manual_seed(1234)
+    return [torch.randint(0, 256, (1, 32), generator=g) for _ in range(8)]
+
+
+def packed(model):
+    return {k: v for k, v in model.state_dict().items() if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales", "input_scale")}
+
+
+def assert_same(got, want):
+    assert set(got) == set(want), sorted(set(got) ^ set(want))[:6]
+    for k, ref in want.items():
+        if ref.dtype == torch.int32:
+            assert (fields(got[k], 4) != fields(ref, 4)).float().mean().item() <= 2e-3, k
+        else:
+            tol = 2e-3 if ref.dtype == torch.float16 else 2e-6
+            assert torch.allclose(got[k].float(), ref.float(), rtol=tol, atol=1e-8), k
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_gptq_matches_live_reference(ref_api, ids, arch, monkeypatch):
+    import neural_compressor_b200.quantization as ours
+    from tests.host_twins import install_gptq_twins
+
+    install_gptq_twins(running_mean=True, setter=monkeypatch.setattr)
+    monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
+    base = build(arch)
+    out = {}
+    for tag, api in (("ref", ref_api), ("ours", ours)):
+        kw = dict(bits=4, group_size=32, use_sym=False, block_size=128)
+        if tag == "ref":
+            kw["model_path"] = "/tmp"
+        m = api.prepare(copy.deepcopy(base), api.GPTQConfig(**kw))
+        for x in ids:
+            m(x)
+        out[tag] = packed(api.convert(m))
+    assert len(out["ref"]) >= 24
+    assert_same(out["ours"], out["ref"])
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_awq_matches_live_reference(ref_api, ids, arch, awq_host_ops):  # noqa: F811
+    import neural_compressor_b200.quantization as ours
+
+    def run_fn(model):
+        for x in ids:
+            model(x)
+
+    base = build(arch)
+    out = {}
+    for tag, api in (("ref", ref_api), ("ours", ours)):
+        m = api.quantize(copy.deepcopy(base), api.AWQConfig(bits=4, group_size=32, use_sym=False), run_fn=run_fn,
+                         example_inputs=ids[0])
+        out[tag] = packed(m)
+    assert len(out["ref"]) >= 24
+    assert_same(out["ours"], out["ref"])
