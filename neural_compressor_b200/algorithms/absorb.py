@@ -239,12 +239,68 @@ def get_shared_input_groups(model, example_inputs) -> Dict[str, List[str]]:
     return groups
 
 
-def get_absorb_layers(model, example_inputs, supported_layers=("Linear",), folding=False):
+def _folds_exactly(model, example_inputs, absorber, linears, rtol=1e-4) -> bool:
+    """Numerical proof that a scale can be folded into `absorber`: put a random per-channel 1/s on its weight (and
+    bias), s on the input channels of the Linears it feeds, and compare the model output on the example input.  Everything
+    is restored afterwards.  This is how module types outside the reference's list are admitted (see `extended`)."""
+    weight = getattr(absorber, "weight", None)
+    if weight is None or weight.dim() != 1 or any(l.in_features != weight.numel() for l in linears):
+        return False
+    device = weight.device
+    inputs = move_to_device(_shrink(example_inputs), device)
+
+    def run():
+        with torch.no_grad():
+            out = model(**inputs) if isinstance(inputs, dict) else (model(*inputs) if isinstance(inputs, (list, tuple)) else model(inputs))
+        out = out[0] if isinstance(out, (tuple, list)) else getattr(out, "logits", out)
+        return out.float()
+
+    g = torch.Generator().manual_seed(0)
+    s = (torch.rand(weight.numel(), generator=g) + 0.5).to(device)
+    saved = [(p, p.detach().clone()) for p in [weight, getattr(absorber, "bias", None)] + [l.weight for l in linears] if p is not None]
+    try:
+        before = run()
+        with torch.no_grad():
+            weight.div_(s.to(weight.dtype))
+            if getattr(absorber, "bias", None) is not None:
+                absorber.bias.div_(s.to(absorber.bias.dtype))
+            for l in linears:
+                l.weight.mul_(s.view(1, -1).to(l.weight.dtype))
+        after = run()
+    finally:
+        with torch.no_grad():
+            for p, v in saved:
+                p.copy_(v)
+    return bool(torch.isfinite(after).all()) and float((after - before).abs().max()) <= rtol * float(before.abs().max() + 1e-12)
+
+
+def get_absorb_layers(model, example_inputs, supported_layers=("Linear",), folding=False, extended=None):
     """utility.py:657-688: ({absorbing module: [absorbed Linear, ...]}, [Linear names nothing can absorb]).  When the
-    forward cannot be observed every Linear is reported as not absorbable, like the reference after a failed trace."""
+    forward cannot be observed every Linear is reported as not absorbable, like the reference after a failed trace.
+
+    `extended` (default: env B200WOQ_ABSORB_EXTENDED=1): the reference admits a fixed list of module types as absorbers
+    (`SUPPORTED_MODULES`: LayerNorm, LlamaRMSNorm, T5LayerNorm, ...), which leaves Mistral / Qwen2 / ... without any.  In
+    extended mode every `*Norm` module with a 1-D weight is a candidate, and a candidate TYPE is admitted only if folding a
+    random scale into one of its instances leaves the model output unchanged (`_folds_exactly`) -- which rejects, e.g.,
+    Gemma's RMSNorm (it multiplies by 1 + weight)."""
+    import os
+
+    if extended is None:
+        extended = os.environ.get("B200WOQ_ABSORB_EXTENDED", "0") == "1"
     all_linears = [n for n, m in model.named_modules() if type(m).__name__ == "Linear"]
-    trace = _trace_model(model, example_inputs)
-    if trace is None:
+    if example_inputs is None:
+        logger.warning("No example_inputs: absorb layer detection is skipped")
+        return {}, all_linears
+    supported = SUPPORTED_MODULES
+    if extended:
+        extra = {type(m).__name__ for m in model.modules()
+                 if type(m).__name__.endswith("Norm") and getattr(getattr(m, "weight", None), "dim", lambda: 0)() == 1}
+        supported = tuple(SUPPORTED_MODULES) + tuple(sorted(extra - set(SUPPORTED_MODULES)))
+    device = next(model.parameters()).device
+    try:
+        trace = EagerTrace(model, supported).run(model, move_to_device(_shrink(example_inputs), device))
+    except Exception as ex:  # pragma: no cover
+        logger.warning(f"Eager trace failed ({type(ex).__name__}: {ex}), absorb layer detection is skipped")
         return {}, all_linears
     absorb_to_layer: Dict[str, List[str]] = {}
     no_absorb: List[str] = []
@@ -259,6 +315,18 @@ def get_absorb_layers(model, example_inputs, supported_layers=("Linear",), foldi
             no_absorb.append(name)
         else:
             absorb_to_layer.setdefault(trace.names[id(parent)], []).append(name)
+    if extended:
+        verdict = {}   # module type outside the reference's list -> does a fold preserve the function?
+        mods = dict(model.named_modules())
+        for key in list(absorb_to_layer):
+            tname = type(mods[key]).__name__
+            if tname in SUPPORTED_MODULES:
+                continue
+            if tname not in verdict:
+                verdict[tname] = _folds_exactly(model, example_inputs, mods[key], [mods[n] for n in absorb_to_layer[key]])
+                logger.info(f"absorb discovery: {tname} {'admitted' if verdict[tname] else 'rejected'} by the fold check")
+            if not verdict[tname]:
+                no_absorb.extend(absorb_to_layer.pop(key))
     if not absorb_to_layer:
         logger.warning("No absorb layer is detected.")
     return absorb_to_layer, no_absorb

@@ -92,6 +92,11 @@ def absorb_scale(layer: torch.nn.Module, scale: torch.Tensor):
         layer.weight.data.mul_(scale.view(-1, 1).to(layer.weight.dtype))
     elif name in ("LlamaRMSNorm", "T5LayerNorm"):
         layer.weight.data.mul_(scale.to(layer.weight.dtype))
+    elif getattr(getattr(layer, "weight", None), "dim", lambda: 0)() == 1 and name.endswith("Norm"):
+        # a norm type admitted by absorb.get_absorb_layers(extended=True) after its numerical fold check
+        layer.weight.data.mul_(scale.to(layer.weight.dtype))
+        if getattr(layer, "bias", None) is not None:
+            layer.bias.data.mul_(scale.to(layer.bias.dtype))
     else:
         raise NotImplementedError(f"cannot fold a smoothing scale into {name}")
 

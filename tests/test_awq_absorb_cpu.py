@@ -144,3 +144,64 @@ def test_awq_host_flow_with_discovered_absorption(host_ops, golden, tag, monkeyp
         assert isinstance(m.layers[0].o, MulLinear) and not isinstance(m.layers[0].q, MulLinear)
     else:   # everything is folded: no run-time multiply anywhere; `o` had nothing to fold into and kept a plain RTN
         assert not any(type(x).__name__ == "MulLinear" for x in m.modules())
+
+
+@pytest.mark.parametrize("arch,admitted", [("mistral", True), ("qwen2", True), ("gemma", False)])
+def test_extended_absorbers_are_admitted_by_execution(arch, admitted):
+    """Beyond the reference's fixed type list: a `*Norm` type is admitted iff folding a random scale into it leaves the
+    model output unchanged -- MistralRMSNorm / Qwen2RMSNorm pass, GemmaRMSNorm (1 + weight) is rejected; the probe restores
+    every weight."""
+    from neural_compressor_b200.algorithms.absorb import get_absorb_layers
+    from tests.test_arch_sweep_cpu import build
+
+    m = build(arch).float().eval()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    ids = torch.randint(0, 256, (2, 24), generator=torch.Generator().manual_seed(0))
+    strict, _ = get_absorb_layers(m, ids, extended=False)
+    assert strict == {}                                      # none of these norm types is in the reference's list
+    found, rest = get_absorb_layers(m, ids, extended=True)
+    assert all(torch.equal(v, m.state_dict()[k]) for k, v in before.items())
+    if not admitted:
+        assert found == {} and len(rest) == 15
+        return
+    p = "model.layers.0."
+    assert found[p + "input_layernorm"] == [p + "self_attn.q_proj", p + "self_attn.k_proj", p + "self_attn.v_proj"]
+    assert found[p + "post_attention_layernorm"] == [p + "mlp.gate_proj", p + "mlp.up_proj"]
+
+
+def test_awq_folding_on_mistral_with_extended_absorbers(host_ops, monkeypatch):
+    """folding=True end to end on an architecture the reference cannot fold at all: scales go into the RMSNorms, no
+    MulLinear is inserted, and the 4-bit model stays close to the fp one."""
+    import neural_compressor_b200.quantization as api
+    from tests.test_arch_sweep_cpu import build
+
+    monkeypatch.setenv("B200WOQ_ABSORB_EXTENDED", "1")
+    g = torch.Generator().manual_seed(1234)
+    ids = [torch.randint(0, 256, (1, 32), generator=g) for _ in range(8)]
+    m = build("mistral").float().eval()
+    with torch.no_grad():
+        fp = m(ids[0]).logits.clone()
+    norm0 = m.model.layers[0].input_layernorm.weight.detach().clone()
+
+    def run_fn(model):
+        for x in ids:
+            model(x)
+
+    # (sym: the reference's recover() wraps int8(q - zp) for 8-bit ASYMMETRIC codes, modules.py:435 -- reproduced by K4/K6 --
+    # so only the symmetric 8-bit format can serve as a "nearly lossless" probe)
+    q = api.quantize(m, api.AWQConfig(bits=8, group_size=32, use_sym=True, folding=True), run_fn=run_fn, example_inputs=ids[0])
+    assert not any(type(x).__name__ == "MulLinear" for x in q.modules())
+    assert not torch.equal(q.model.layers[0].input_layernorm.weight, norm0)
+    packed = {n: x for n, x in q.named_modules() if type(x).__name__ == "B200WeightOnlyLinear"}
+    assert len(packed) == 14       # folded q/k/v + gate/up, and o_proj / down_proj (no absorber: plain RTN) in both blocks
+    # evaluate the packed model on the host: recover every weight with the oracle and run dense linears
+    from neural_compressor_b200.utils import set_module
+    from oracle import woq_oracle as O
+
+    for n, x in packed.items():
+        lin = torch.nn.Linear(x.in_features, x.out_features, bias=False)
+        lin.weight.data = O.recover_fp16(x.qweight, x.qzeros, x.scales, x.bits, x.group_size, x.in_features, x.out_features).float()
+        set_module(q, n, lin)
+    with torch.no_grad():
+        out = q(ids[0]).logits
+    assert float((out - fp).norm() / fp.norm()) < 6e-2      # 8-bit weights (+ clip search, fp16 scales): still the same function
