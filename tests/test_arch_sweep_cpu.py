@@ -113,3 +113,48 @@ def test_awq_matches_live_reference(ref_api, ids, arch, awq_host_ops):  # noqa: 
         out[tag] = packed(m)
     assert len(out["ref"]) >= 24
     assert_same(out["ours"], out["ref"])
+
+
+@pytest.mark.parametrize("arch", ["falcon", "bloom", "phi", "mpt", "qwen2"])
+def test_smoothquant_transform_matches_live_reference(ref_api, ids, arch, monkeypatch):
+    """`TorchSmoothQuant.transform` of the live reference (IPEX stubbed) vs algorithms/smooth_quant.py (kernels = oracle
+    twins): same modules smoothed, same smoothing scales, same static activation qparams."""
+    from neural_compressor_b200 import ops
+    from neural_compressor_b200.algorithms import smooth_quant as sq
+    from oracle import woq_oracle as O
+    from oracle.ref_loader import load_smooth_quant_utility
+    import neural_compressor_b200.quantization as ours
+
+    SQ = load_smooth_quant_utility()
+
+    def minmax_cols_accumulate(X, mx, mn):
+        X2 = X.reshape(-1, X.shape[-1]).float()
+        mx.copy_(torch.maximum(mx, X2.max(0)[0]))
+        mn.copy_(torch.minimum(mn, X2.min(0)[0]))
+
+    def sq_smooth_quant_weight(W, smooth):
+        _, q, s = O.sq_qdq_weight_per_channel(W.float() * smooth.view(1, -1))
+        return dict(qweight=q.to(torch.int8), w_scale=s.flatten().float(), wsum=q.sum(1).to(torch.int32))
+
+    monkeypatch.setattr(ops, "minmax_cols_accumulate", minmax_cols_accumulate)
+    monkeypatch.setattr(ops, "sq_smooth_quant_weight", sq_smooth_quant_weight)
+    monkeypatch.setattr(sq, "current_device", lambda: torch.device("cpu"))
+    base = build(arch)
+
+    def q_func(model):
+        for t in ids:
+            model(t)
+
+    m = copy.deepcopy(base)
+    m = SQ.TorchSmoothQuant(m, dataloader=None, example_inputs=ids[0], q_func=q_func).transform(
+        alpha=0.5, folding=False, calib_iter=len(ids), op_types=[torch.nn.Linear])
+    want = {n: x for n, x in m.named_modules() if type(x).__name__ == "SQLinearWrapper"}
+    q = sq.SmoothQuantQuantizer(ours.SmoothQuantConfig(alpha=0.5), absorb_discovery="off")
+    mo = q.prepare(copy.deepcopy(base), example_inputs=ids[0])
+    with torch.no_grad():
+        q_func(mo)
+    got = {n: x for n, x in q.convert(mo).named_modules() if isinstance(x, sq.SQLinear)}
+    assert set(got) == set(want) and len(want) >= 9
+    for n, ref in want.items():
+        assert torch.equal(got[n].input_scale, ref.input_scale), n
+        assert float(got[n].x_scale) == float(ref.scale) and int(got[n].x_zp) == int(ref.zero_point), n
