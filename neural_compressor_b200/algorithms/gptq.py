@@ -49,6 +49,9 @@ def trace_gptq_target_blocks(model):
             found = True
         elif not found and len(list(module.children())) == 0:
             info["embeddings"][name] = module
+        elif found and name.find(info["transformers_name"]) == -1:
+            # gptq.py:122-125: every module after the stack overwrites the entry, so the LAST one (lm_head) wins
+            info["transformers_post"] = {"name": name, "layer": module}
     if not found:
         raise ValueError("GPTQ needs a model with an nn.ModuleList of transformer blocks")
     return info
@@ -429,7 +432,74 @@ class RAWGPTQuantizer:
             if cb is not None:
                 cb(block_idx)
         self._check_factor_status()
+        if self.quant_lm_head:
+            self.quantize_post_layer()
         return self.model
+
+    @torch.no_grad()
+    def quantize_post_layer(self):
+        """gptq.py:886-1078 (`quant_lm_head=True`): the module after the transformer stack (lm_head) goes through the same
+        Hessian -> factor -> column loop -> pack chain.  As in the reference its calibration inputs are the outputs of the
+        LAST block as they sit in the cache -- the final norm of the model is not applied (gptq.py:929-933)."""
+        import torch.distributed as dist
+
+        post = self.blocks_info.get("transformers_post") or {}
+        name, layer = post.get("name"), post.get("layer")
+        if layer is None or not (isinstance(layer, torch.nn.Linear) or _is_conv1d(layer)):
+            logger.warning("quant_lm_head: no Linear found after the transformer stack; nothing to do")
+            return
+        cfg = self.get_layer_config(name)
+        if cfg is None:
+            logger.warning(f"{name} can be quantized but excluded from quantization configs.")
+            return
+        if cfg.get("fp8_aware") or cfg.get("static_groups"):
+            raise NotImplementedError("fp8_aware / static_groups are not available for the post-transformer layer")
+        logger.info("Quantizing post transformer layers")
+        layer.to(self.device)
+        hs = self.cache_kwargs["hidden_states"] if "hidden_states" in self.cache_kwargs else self.cache_args[0]
+        C = hs[0].shape[-1]
+        Hsum = torch.zeros((C, C), dtype=torch.float32, device=self.device)
+        local_n = 0
+        for x in hs:
+            x = x.to(self.device)
+            ops.hessian_accumulate(x if x.is_contiguous() else x.contiguous(), Hsum)
+            local_n += x.shape[0] if x.dim() == 3 else 1
+        if _dist_world() > 1:
+            dist.all_reduce(Hsum, op=dist.ReduceOp.SUM)
+        nsamples = self._global_nsamples(local_n)
+        Hc, dead = ops.hessian_finalize(Hsum, nsamples, cfg["percdamp"])
+        perm = None
+        if cfg["act_order"]:
+            perm = torch.argsort(torch.diag(Hc), descending=True)
+        elif cfg.get("hybrid_order"):
+            perm = hybrid_order_perm(torch.diag(Hc), int(cfg["group_size"]))
+        if perm is not None:
+            Hc = Hc[perm][:, perm].contiguous()
+            dead = dead[perm].contiguous()
+        Hinv = ops.cholesky_inverse_upper(Hc)
+        W = layer.weight.data
+        W = (W.t() if _is_conv1d(layer) else W).float()
+        W = (W[:, perm] if perm is not None else W).contiguous().clone()
+        r = self._fasterquant_rows_sharded(W, Hinv, dead, cfg)
+        g_idx = None
+        if perm is not None:
+            inv = torch.argsort(perm)
+            r["codes"] = r["codes"][:, inv].contiguous()
+            if cfg["act_order"]:
+                g_idx = perm
+            else:
+                g = int(cfg["group_size"])
+                inv_order = torch.argsort(perm[::g] // g)
+                r["scale"], r["zero"] = r["scale"][:, inv_order].contiguous(), r["zero"][:, inv_order].contiguous()
+        if _is_conv1d(layer):
+            in_f, out_f = layer.weight.shape[0], layer.weight.shape[1]
+        else:
+            in_f, out_f = layer.in_features, layer.out_features
+        new_module = B200WeightOnlyLinear(in_f, out_f, dtype=cfg["dtype"], bits=cfg["bits"], group_size=cfg["group_size"],
+                                          zp=not cfg["sym"], bias=layer.bias is not None, g_idx=g_idx is not None,
+                                          device=self.device)
+        new_module.pack_stored(r["codes"], r["scale"], None if cfg["sym"] else r["zero"], layer.bias, g_idx=g_idx)
+        set_module(self.model, name, new_module)
 
     @torch.no_grad()
     def _side_streams(self, n):

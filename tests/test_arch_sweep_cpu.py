@@ -158,3 +158,39 @@ def test_smoothquant_transform_matches_live_reference(ref_api, ids, arch, monkey
     for n, ref in want.items():
         assert torch.equal(got[n].input_scale, ref.input_scale), n
         assert float(got[n].x_scale) == float(ref.scale) and int(got[n].x_zp) == int(ref.zero_point), n
+
+
+def test_gptq_quant_lm_head_vs_live_reference(ref_api, monkeypatch):
+    """`GPTQConfig(quant_lm_head=True)` (gptq.py:886-1078).  All block tensors must coincide with the live reference.  The
+    lm_head itself cannot: in the prepare()/convert() flow the reference feeds `range(len(self.dataloader))` = 0 batches
+    to the lm_head Hessian (gptq.py:283, 935), so every column counts as dead, the weight is zeroed and the packed lm_head
+    dequantises to all zeros (scales = 2/15 everywhere).  Here the cached outputs of the last block are used, as that loop
+    intends, and the packed lm_head is a 4-bit image of the real weight."""
+    import neural_compressor_b200.quantization as ours
+    from oracle import woq_oracle as O
+    from oracle.gen_golden import tiny_llama
+    from tests.host_twins import install_gptq_twins
+
+    install_gptq_twins(running_mean=True, setter=monkeypatch.setattr)
+    monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
+    g = torch.Generator().manual_seed(1234)
+    ids = [torch.randint(0, 512, (1, 32), generator=g) for _ in range(8)]
+    base = tiny_llama()
+    out = {}
+    for tag, api in (("ref", ref_api), ("ours", ours)):
+        kw = dict(bits=4, group_size=32, use_sym=False, block_size=128, quant_lm_head=True)
+        if tag == "ref":
+            kw["model_path"] = "/tmp"
+        m = api.prepare(copy.deepcopy(base), api.GPTQConfig(**kw))
+        for x in ids:
+            m(x)
+        out[tag] = packed(api.convert(m))
+    assert set(out["ours"]) == set(out["ref"]) and "lm_head.qweight" in out["ref"]
+    blocks = {k: v for k, v in out["ref"].items() if not k.startswith("lm_head")}
+    assert_same({k: out["ours"][k] for k in blocks}, blocks)
+    ref_scales = out["ref"]["lm_head.scales"].float()
+    assert torch.allclose(ref_scales, torch.full_like(ref_scales, 2 / 15), rtol=1e-3)        # the degenerate all-dead result
+    w = O.recover_fp16(out["ours"]["lm_head.qweight"], out["ours"]["lm_head.qzeros"], out["ours"]["lm_head.scales"], 4, 32,
+                       128, 512).float()
+    w0 = base.lm_head.weight.detach()
+    assert float((w - w0).norm() / w0.norm()) < 0.15
