@@ -194,3 +194,47 @@ def test_gptq_quant_lm_head_vs_live_reference(ref_api, monkeypatch):
                        128, 512).float()
     w0 = base.lm_head.weight.detach()
     assert float((w - w0).norm() / w0.norm()) < 0.15
+
+
+def test_mixed_rtn_and_gptq_composable_config_vs_live_reference(ref_api, monkeypatch):
+    """The reference's test_mixed_algos.py: `RTNConfig(white_list=[".*mlp.*"]) + GPTQConfig(white_list=[".*attn.*"])` in
+    one `quantize()` call -- RTN packs the MLPs first, GPTQ then calibrates the attention linears THROUGH the packed MLPs."""
+    import neural_compressor.torch.algorithms.layer_wise as LW
+    import neural_compressor.torch.algorithms.layer_wise.utils as LU
+    import neural_compressor_b200.quantization as ours
+    from neural_compressor_b200 import ops
+    from neural_compressor_b200.algorithms import rtn
+    from oracle import woq_oracle as O
+    from oracle.gen_golden import family_models
+    from tests.host_twins import install_gptq_twins
+
+    install_gptq_twins(running_mean=True, setter=monkeypatch.setattr)
+    monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
+
+    def rtn_quant_pack(W, bits=4, group_size=-1, sym=False, full_range=False, quantile=1.0, return_codes=False):
+        q, s, z = O.rtn_quantize(W, bits, group_size, "sym" if sym else "asym", quantile, full_range)
+        qweight, qzeros, scales16 = O.pack_optimum(q, s, z, bits, group_size)
+        return dict(qweight=qweight, qzeros=qzeros, scales=scales16, scale_f32=s.float(), zp_f32=None if z is None else z.float())
+
+    def woq_linear(x, qweight, qzeros, scales, bias, bits, group_size, in_features, out_features, g_idx=None,
+                   input_scale=None, out_dtype=None, flags=0):
+        xx = x if input_scale is None else x * input_scale
+        y = O.woq_linear_forward(xx, qweight, qzeros, scales, bias, bits, group_size, in_features, out_features, g_idx)
+        return y.to(out_dtype or x.dtype)
+
+    monkeypatch.setattr(ops, "rtn_quant_pack", rtn_quant_pack)
+    monkeypatch.setattr(ops, "woq_linear", woq_linear)
+    monkeypatch.setattr(rtn, "current_device", lambda: torch.device("cpu"))
+    # a random-init model has no checkpoint path for the reference's layer-wise helper to resolve
+    for mod in (LU, LW):
+        if hasattr(mod, "get_path"):
+            monkeypatch.setattr(mod, "get_path", lambda p: "/tmp")
+    base = family_models()("gptj")
+    tokens = torch.tensor([[10, 20, 30, 40, 50, 60, 70, 80, 90, 100, 110, 120]], dtype=torch.long)
+    out = {}
+    for tag, api in (("ref", ref_api), ("ours", ours)):
+        cfg = api.RTNConfig(white_list=[".*mlp.*"]) + api.GPTQConfig(double_quant_bits=4, white_list=[".*attn.*"])
+        m = api.quantize(copy.deepcopy(base), cfg, run_fn=lambda model: model(tokens))
+        out[tag] = packed(m)
+    assert len(out["ref"]) == 36
+    assert_same(out["ours"], out["ref"])
