@@ -96,7 +96,7 @@ def _load_huggingface(model_dir, device="cuda", **kwargs):
             state.update(load_file(fn, device=str(device)))
     else:
         for fn in sorted(glob.glob(os.path.join(model_dir, "pytorch_model*.bin"))):
-            state.update(torch.load(fn, map_location=device))
+            state.update(torch.load(fn, map_location=device, weights_only=True))
     assert state, f"no weight shards under {model_dir}"
     # an uninitialised model of the right architecture (the stored config must not re-trigger HF's own GPTQ loader)
     plain = AutoConfig.from_pretrained(model_dir, trust_remote_code=kwargs.get("trust_remote_code", False))
@@ -175,7 +175,8 @@ def load(model_name_or_path, original_model=None, format="default", device="cuda
 
     with open(os.path.join(model_name_or_path, QCONFIG_NAME)) as f:
         qcfg = json.load(f)
-    state = torch.load(os.path.join(model_name_or_path, WEIGHT_NAME), map_location=device)
+    # tensors only, never pickled code (the reference's `_load_weight_file`, save_load.py: weights_only=True)
+    state = torch.load(os.path.join(model_name_or_path, WEIGHT_NAME), map_location=device, weights_only=True)
     model = original_model.to(device)
     # Which modules are packed is decided by the checkpoint (`<name>.qweight` present), not by the qconfig dtype: the
     # GPTQ engine mirrors the reference's `get_layer_config` fallback (gptq.py:367-382), which quantises in-block

@@ -166,3 +166,26 @@ def test_autoawq_checkpoint_loads_through_the_huggingface_loader(tmp_path):
         assert torch.equal(sd[k], ref), k
         n += 1
     assert n == 42 and isinstance(loaded.model.layers[0].self_attn.q_proj, B200WeightOnlyLinear)
+
+
+def test_default_format_load_reads_tensors_only(tmp_path, monkeypatch):
+    """The reference's loader passes weights_only=True to torch.load (test_load.py:111-128): a checkpoint is data."""
+    import json
+
+    import torch
+
+    from neural_compressor_b200.algorithms import save_load
+
+    calls = []
+    real = torch.load
+
+    def spy(path, **kwargs):
+        calls.append(kwargs)
+        return real(path, **kwargs)
+
+    torch.save({"weight": torch.ones(2, 2), "bias": torch.zeros(2)}, tmp_path / save_load.WEIGHT_NAME)
+    json.dump({}, open(tmp_path / save_load.QCONFIG_NAME, "w"))
+    monkeypatch.setattr(torch, "load", spy)
+    m = save_load.load(str(tmp_path), original_model=torch.nn.Linear(2, 2), device="cpu")
+    assert calls and all(c.get("weights_only") is True for c in calls)
+    assert torch.equal(m.weight, torch.ones(2, 2))
