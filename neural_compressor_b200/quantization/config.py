@@ -353,6 +353,22 @@ def get_default_rtn_config():
     return RTNConfig()
 
 
+# torch/utils/constants.py:18-42: named double-quantisation presets of RTN
+DOUBLE_QUANT_CONFIGS = {
+    "BNB_NF4": {"dtype": "nf4", "bits": 4, "group_size": 32, "use_double_quant": True, "double_quant_bits": 8,
+                "double_quant_dtype": "int", "double_quant_use_sym": False, "double_quant_group_size": 256},
+    "GGML_TYPE_Q4_K": {"dtype": "int", "bits": 4, "use_sym": False, "group_size": 32, "use_double_quant": True,
+                       "double_quant_bits": 6, "double_quant_dtype": "int", "double_quant_use_sym": True,
+                       "double_quant_group_size": 8},
+}
+
+
+def get_default_double_quant_config(type="BNB_NF4"):
+    """config.py:305-317."""
+    assert type in DOUBLE_QUANT_CONFIGS, "Supported double quant configs: {}".format(list(DOUBLE_QUANT_CONFIGS.keys()))
+    return RTNConfig.from_dict(DOUBLE_QUANT_CONFIGS[type])
+
+
 def get_default_gptq_config():
     return GPTQConfig()
 

@@ -142,3 +142,18 @@ def test_side_by_side_with_the_live_reference():
     cr = ref.RTNConfig(bits=8, white_list=["fc1"]) + ref.GPTQConfig(bits=3, white_list=["fc2"])
     assert {k: (v.name, v.bits) for k, v in co.to_config_mapping(model_info=co.get_model_info(model)).items()} == \
         {k: (v.name, v.bits) for k, v in cr.to_config_mapping(model_info=cr.get_model_info(model)).items()}
+
+
+def test_double_quant_presets_match_the_reference():
+    for preset in ("BNB_NF4", "GGML_TYPE_Q4_K"):
+        c = ours.get_default_double_quant_config(preset)
+        assert c.use_double_quant and isinstance(c, ours.RTNConfig)
+    assert ours.get_default_double_quant_config().dtype == "nf4"
+    with pytest.raises(AssertionError):
+        ours.get_default_double_quant_config("Q8")
+    live = reference_api()
+    if live is not None:
+        ref, _ = live
+        for preset in ("BNB_NF4", "GGML_TYPE_Q4_K"):
+            a, b = ours.get_default_double_quant_config(preset), ref.get_default_double_quant_config(preset)
+            assert all(getattr(a, k) == getattr(b, k) for k in ours.RTNConfig.params_list), preset
