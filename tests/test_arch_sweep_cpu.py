@@ -238,3 +238,35 @@ def test_mixed_rtn_and_gptq_composable_config_vs_live_reference(ref_api, monkeyp
         out[tag] = packed(m)
     assert len(out["ref"]) == 36
     assert_same(out["ours"], out["ref"])
+
+
+def test_exotic_parameter_corners_vs_live_reference(ref_api, monkeypatch):
+    """Corners of the reference's parameter matrices (test_gptq.py:106-135, test_awq.py:60-84) on the tiny llama: 2-bit
+    group-8 act_order GPTQ with the default block_size 2048."""
+    import neural_compressor_b200.quantization as ours
+    from oracle.gen_golden import tiny_llama
+    from tests.host_twins import install_gptq_twins
+
+    install_gptq_twins(running_mean=True, setter=monkeypatch.setattr)
+    monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
+    g = torch.Generator().manual_seed(1234)
+    ids = [torch.randint(0, 512, (1, 32), generator=g) for _ in range(8)]
+    base = tiny_llama()
+    out = {}
+    for tag, api in (("ref", ref_api), ("ours", ours)):
+        kw = dict(bits=2, use_sym=True, group_size=8, act_order=True)
+        if tag == "ref":
+            kw["model_path"] = "/tmp"
+        m = api.prepare(copy.deepcopy(base), api.GPTQConfig(**kw))
+        for x in ids:
+            m(x)
+        m = api.convert(m)
+        out[tag] = {k: v for k, v in m.state_dict().items() if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales", "g_idx")}
+    assert set(out["ours"]) == set(out["ref"]) and len(out["ref"]) == 56
+    for k, ref in out["ref"].items():
+        if k.endswith("g_idx"):
+            assert torch.equal(out["ours"][k], ref), k
+        elif ref.dtype == torch.int32:
+            assert (fields(out["ours"][k], 2) != fields(ref, 2)).float().mean().item() <= 2e-3, k
+        else:
+            assert torch.allclose(out["ours"][k].float(), ref.float(), rtol=2e-3, atol=1e-8), k
