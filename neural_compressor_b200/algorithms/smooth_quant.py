@@ -101,6 +101,174 @@ def absorb_scale(layer: torch.nn.Module, scale: torch.Tensor):
         raise NotImplementedError(f"cannot fold a smoothing scale into {name}")
 
 
+def _qdq_weight(w):
+    """quant_dequant_w_v1 (:652-690), nn.Linear, symmetric int8 per output channel."""
+    eps = torch.finfo(torch.float32).eps
+    scale = torch.clip(torch.max(torch.abs(w), dim=1).values / (255.0 / 2), min=eps).unsqueeze(-1)
+    return torch.round(w / scale).clamp_(-128.0, 127.0) * scale
+
+
+def _qdq_act(x, min_x, max_x):
+    """quant_dequant_x_v1 (:726-755): asymmetric uint8 over the given (per-tensor) range."""
+    eps = torch.finfo(torch.float32).eps
+    max_x, min_x = torch.max(max_x), torch.min(min_x)
+    scale = torch.clip((max_x - min_x) / 255, min=eps)
+    bias = torch.round((0 - min_x) / scale)
+    return scale * (torch.round(x / scale + bias).clamp_(0, 255.0) - bias)
+
+
+class _QDQProbe(torch.nn.Module):
+    """`WrapperLayer` (:2665-2755): a Linear that can run its W8A8 quant-dequant simulation for a given smoothing scale
+    and remembers the (upstream-quantised) input and the output of its last call -- what the alpha search compares."""
+
+    def __init__(self, layer, input_min, input_max):
+        super().__init__()
+        self.add_module("orig_layer", layer)
+        self.quant = False
+        self.q_input = self.output = None
+        self.input_min, self.input_max = input_min, input_max
+        self.input_scale = self.weight_scale = None
+
+    def q_dq_forward(self, x, input_scale, weight_scale):
+        dtype = x.dtype      # the simulation runs in fp32 (the reference's only mode); a half model gets its dtype back
+        x = x.float()
+        w = self.orig_layer.weight.detach().float()
+        w = _qdq_weight(w * weight_scale if weight_scale is not None else w)
+        if input_scale is None:
+            x = _qdq_act(x, self.input_min, self.input_max)
+        else:
+            x = _qdq_act(input_scale * x, self.input_min * input_scale, self.input_max * input_scale)
+        bias = self.orig_layer.bias
+        return torch.nn.functional.linear(x, w, None if bias is None else bias.float()).to(dtype)
+
+    def forward(self, x):
+        if self.quant:
+            self.q_input = x
+            out = self.q_dq_forward(x, self.input_scale, self.weight_scale)
+        else:
+            out = self.orig_layer(x)
+        self.output = out
+        return out
+
+
+def _auto_loss(output, output_q):
+    """`_get_auto_loss` (:1483-1507), loss_type "abs": sum |o/max - o_q/max|^0.5 with a per-sample max."""
+    if output.dim() <= 2:
+        max_value = torch.max(torch.abs(output))
+    else:
+        output = output.reshape(output.shape[0], -1)
+        output_q = output_q.reshape(output_q.shape[0], -1)
+        max_value = torch.clip(torch.max(torch.abs(output), dim=-1).values.unsqueeze(-1), 1e-5)
+    return torch.sum(torch.pow(torch.abs(output / max_value - output_q / max_value), 0.5))
+
+
+def auto_tune_alpha(model, groups, stats, batches, alpha_min=0.0, alpha_max=1.0, alpha_step=0.1, init_alpha=0.5,
+                    shared_criterion="mean", n_samples=32, **_unused):
+    """`AutoAlpha._auto_tune_alpha` (:1751-1820), model-wise: per scale-sharing group the alpha whose W8A8 simulation
+    stays closest to the fp output of its layers.
+
+    groups  {key: [Linear names]}; stats {name: (max, min)} per input channel; batches: the model inputs seen during
+    calibration (a list of (args, kwargs)).  Returns {key: alpha}.  Notes that matter for agreeing with the reference:
+    the losses of ONE batch decide (its `loss_alphas` is re-created per batch, :1776), the running choice is refreshed every
+    n_samples // 4 batches and determines the upstream quantisation the probes see, ties keep the reference's dict order
+    (current alpha first, then the grid)."""
+    import numpy
+
+    digits = max(len(str(v).split(".")[1]) for v in (alpha_min, alpha_max, alpha_step))
+    alpha_space = numpy.round(numpy.arange(alpha_min, alpha_max + alpha_step, alpha_step), digits).tolist()
+    modules = dict(model.named_modules())
+    names = [n for v in groups.values() for n in v]
+    probes = {}
+    for n in names:
+        mx, mn = stats[n]
+        probes[n] = _QDQProbe(modules[n], mn, mx)
+        set_module(model, n, probes[n])
+
+    def scales_for(alpha):
+        out = {}
+        for key, members in groups.items():
+            a = alpha[key] if isinstance(alpha, dict) else alpha
+            mx, mn = stats[members[0]]
+            s = cal_scale(torch.maximum(mx.abs(), mn.abs()), [probes[n].orig_layer.weight.data.float() for n in members], a)
+            inv = 1.0 / s
+            inv[s == 0] = 0
+            for n in members:
+                out[n] = (inv.view(1, -1), s.view(1, -1))
+        return out
+
+    def apply(alpha):
+        for n, (i, w) in scales_for(alpha).items():
+            probes[n].input_scale, probes[n].weight_scale = i, w
+
+    def run(batch):
+        args, kwargs = batch
+        model(*args, **kwargs)
+
+    def best_of(losses):
+        best = {}
+        for key, members in groups.items():
+            crit = "min" if len(members) == 1 else shared_criterion
+            if crit == "mean":
+                total = {}
+                for a in losses[members[0]]:
+                    total[a] = sum(losses[n][a] for n in members)
+                best[key] = float(sorted(total.items(), key=lambda kv: kv[1])[0][0])
+            elif crit in ("min", "max"):
+                picks = [float(sorted(losses[n].items(), key=lambda kv: kv[1])[0][0]) for n in members]
+                best[key] = min(picks) if crit == "min" else max(picks)
+            else:
+                raise NotImplementedError(crit)
+        return best
+
+    try:
+        apply(init_alpha)
+        best = init_alpha
+        every = n_samples // 4 if n_samples >= 4 else n_samples
+        seen = since = 0
+        losses = None
+        for batch in batches:
+            per_module = best
+            if isinstance(best, dict):
+                per_module = dict(best)
+                for key, members in groups.items():
+                    for n in members:
+                        per_module[n] = best[key]
+            for p in probes.values():
+                p.quant = False
+            run(batch)
+            fp_out = {n: probes[n].output for n in names}
+            for p in probes.values():
+                p.quant = True
+            apply(per_module if not isinstance(per_module, dict) else {k: per_module[k] for k in groups})
+            run(batch)
+            losses = {}
+            for n in names:
+                cur = per_module[n] if isinstance(per_module, dict) else per_module
+                losses[n] = {str(cur): _auto_loss(fp_out[n], probes[n].output)}
+            for a in alpha_space:
+                sc = scales_for(a)
+                for n in names:
+                    if str(a) in losses[n]:
+                        continue
+                    i, w = sc[n]
+                    losses[n][str(a)] = _auto_loss(fp_out[n], probes[n].q_dq_forward(probes[n].q_input, i, w))
+                # the probes keep the grid's last scales, exactly like the reference's `_update_scales_for_auto` calls
+                for n, (i, w) in sc.items():
+                    probes[n].input_scale, probes[n].weight_scale = i, w
+            seen += 1
+            since += 1
+            if since // every >= 1:
+                since = 0
+                best = best_of(losses)
+                apply(best)
+            if seen >= n_samples:
+                break
+        return best_of(losses) if losses is not None else {k: init_alpha for k in groups}
+    finally:
+        for n, p in probes.items():
+            set_module(model, n, p.orig_layer)
+
+
 class SmoothQuantQuantizer(Quantizer):
     """Calibrate -> group -> smooth -> static W8A8 modules.
 
@@ -124,6 +292,13 @@ class SmoothQuantQuantizer(Quantizer):
         model.to(self.device)
         self.example_inputs = example_inputs
         self._stats, self._handles = {}, []
+        self._batches = []           # model-level inputs of the calibration run, for alpha="auto" (build_captured_dataloader)
+
+        def remember(_m, args, kwargs):
+            if len(self._batches) < 128:
+                self._batches.append((args, kwargs))
+
+        self._handles.append(model.register_forward_pre_hook(remember, with_kwargs=True))
         for name, m in model.named_modules():
             if isinstance(m, torch.nn.Linear):
                 k = m.in_features
@@ -157,10 +332,11 @@ class SmoothQuantQuantizer(Quantizer):
         for h in self._handles:
             h.remove()
         alpha = self.quant_config.alpha
-        if isinstance(alpha, str):
-            logger.warning("alpha='auto' (the reference's AutoAlpha search) is not built; using 0.5")
-            alpha = 0.5
-        alpha = float(alpha)
+        auto = isinstance(alpha, str)
+        if auto:
+            assert alpha == "auto", f"alpha must be a number or 'auto', got {alpha!r}"
+        else:
+            alpha = float(alpha)
         folding = bool(getattr(self.quant_config, "folding", False))
         for name, (mx, _mn) in self._stats.items():
             if torch.isinf(mx).any():
@@ -169,12 +345,21 @@ class SmoothQuantQuantizer(Quantizer):
         if folding and not groups:
             logger.warning("empty absorb_to_layer, smoothquant is ignored")   # utility.py:2367-2369
         modules = dict(model.named_modules())
+        if auto:   # per-group alpha from the W8A8 simulation (AutoAlpha, :1232-1893; model-wise search)
+            args = dict(getattr(self.quant_config, "auto_alpha_args", None) or {})
+            if args.pop("do_blockwise", False):
+                raise NotImplementedError("blockwise auto-alpha tuning is not built (model-wise only)")
+            alpha = auto_tune_alpha(model, groups, self._stats, self._batches, **args)
+            for key, a in alpha.items():
+                logger.info(f"Final alpha {key}:{a}")
+            self.tuned_alpha = alpha
         # all scales come from the un-modified weights (`_cal_scales`, :2122-2156) ...
         scales = {}
         for key, names in groups.items():
             mx, mn = self._stats[names[0]]                # the group shares one input (:2132-2136, 2182)
             in_max_abs = torch.maximum(mx.abs(), mn.abs())
-            scales[key] = cal_scale(in_max_abs, [modules[n].weight.data.float() for n in names], alpha)
+            scales[key] = cal_scale(in_max_abs, [modules[n].weight.data.float() for n in names],
+                                    alpha[key] if isinstance(alpha, dict) else alpha)
         # ... then every fold goes into the still-fp producers (a producer may itself be a smoothed Linear: fc1 takes
         # fc2's 1/s on its rows and its own s on its columns) ...
         if folded:

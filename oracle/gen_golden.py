@@ -576,6 +576,20 @@ def gen_sq_transform():
     probe = torch.randint(0, 512, (1, 16), generator=torch.Generator().manual_seed(99))
     run("llama_insert_mul", tiny_llama, ids, probe, folding=False)
     out["llama_ids"], out["llama_probe"] = ids, probe
+    # alpha="auto": AutoAlpha's model-wise search (:1232-1893); the tuned per-group alphas
+    out["auto"] = {}
+    for tag, build, data, args in [
+            ("toy_mean", toy, awq["ids"], dict(init_alpha=0.5, alpha_min=0.0, alpha_max=1.0, alpha_step=0.1, shared_criterion="mean", n_samples=8)),
+            ("toy_max", toy, awq["ids"], dict(init_alpha=0.5, alpha_min=0.3, alpha_max=0.7, alpha_step=0.05, shared_criterion="max", n_samples=6)),
+            ("llama_mean", tiny_llama, ids, dict(init_alpha=0.5, alpha_min=0.0, alpha_max=1.0, alpha_step=0.1, shared_criterion="mean", n_samples=8))]:
+        def q_func(model, data=data):
+            for t in data:
+                model(t)
+
+        sq = SQ.TorchSmoothQuant(build(), dataloader=None, example_inputs=data[0], q_func=q_func)
+        sq.transform(alpha="auto", folding=False, calib_iter=8, op_types=[torch.nn.Linear], auto_alpha_args=dict(args))
+        out["auto"][tag] = dict(args=args, alpha=dict(sq.alpha))
+        print("sq_transform: auto", tag, list(sq.alpha.items())[:3])
     torch.save(out, os.path.join(OUT, "sq_transform.pt"))
 
 

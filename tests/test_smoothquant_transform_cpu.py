@@ -148,3 +148,32 @@ def test_llama_per_layer_fallback(host_ops, golden):
     case = golden["models"]["llama_insert_mul"]
     m = run_ours(tiny_llama(e2e["init_state"]), golden["llama_ids"], "off", alpha=0.5, folding=False)
     check_wrappers(m, case)
+
+
+@pytest.mark.parametrize("tag", ["toy_mean", "toy_max", "llama_mean"])
+def test_auto_alpha_matches_reference(host_ops, golden, toy_data, tag):
+    """`SmoothQuantConfig(alpha="auto")`: AutoAlpha's model-wise search (smooth_quant/utility.py:1232-1893) -- per
+    scale-sharing group the alpha whose W8A8 quant-dequant simulation stays closest to the fp output -- must pick the
+    alphas the live reference picked (fixture written by `TorchSmoothQuant.transform(alpha="auto")`)."""
+    import neural_compressor_b200.quantization as api
+    from neural_compressor_b200.algorithms.smooth_quant import SmoothQuantQuantizer, SQLinear
+
+    case = golden["auto"][tag]
+    if tag.startswith("toy"):
+        model = Toy(d=64, n=2, variant=0, vocab=64).eval()
+        model.load_state_dict(toy_data["init_state"])
+        ids, mode = toy_data["ids"], "eager"
+    else:
+        from tests.test_api_gpu import tiny_llama
+
+        e2e = torch.load(os.path.join(HERE, "golden", "e2e_tiny_llama.pt"))
+        model, ids, mode = tiny_llama(e2e["init_state"]), golden["llama_ids"], "off"
+    q = SmoothQuantQuantizer(api.SmoothQuantConfig(alpha="auto", auto_alpha_args=dict(case["args"])), absorb_discovery=mode)
+    model = q.prepare(model, example_inputs=ids[0])
+    with torch.no_grad():
+        for t in ids:
+            model(t)
+    model = q.convert(model)
+    assert q.tuned_alpha == case["alpha"]
+    assert sum(isinstance(m, SQLinear) for m in model.modules()) >= len(case["alpha"])
+    assert not any(type(m).__name__ == "_QDQProbe" for m in model.modules())       # the probes are gone again
