@@ -226,7 +226,9 @@ def test_mixed_rtn_and_gptq_composable_config_vs_live_reference(ref_api, monkeyp
     monkeypatch.setattr(ops, "woq_linear", woq_linear)
     monkeypatch.setattr(rtn, "current_device", lambda: torch.device("cpu"))
     # a random-init model has no checkpoint path for the reference's layer-wise helper to resolve
-    for mod in (LU, LW):
+    import neural_compressor.torch.algorithms.weight_only.gptq as RG
+
+    for mod in (LU, LW, RG):
         if hasattr(mod, "get_path"):
             monkeypatch.setattr(mod, "get_path", lambda p: "/tmp")
     base = family_models()("gptj")
