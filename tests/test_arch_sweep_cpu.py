@@ -97,7 +97,7 @@ def test_gptq_matches_live_reference(ref_api, ids, arch, monkeypatch):
     assert_same(out["ours"], out["ref"])
 
 
-@pytest.mark.parametrize("arch", ARCHS)
+@pytest.mark.parametrize("arch", ["falcon", "bloom", "gpt_neox", "phi", "qwen2"])
 def test_awq_matches_live_reference(ref_api, ids, arch, awq_host_ops):  # noqa: F811
     import neural_compressor_b200.quantization as ours
 

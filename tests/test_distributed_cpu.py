@@ -251,8 +251,7 @@ def _empty_tiny_llama():
                                         tie_word_embeddings=False))
 
 
-@pytest.mark.parametrize("layer_sharded,extra", [(False, None), (True, None), (False, dict(hybrid_order=True)),
-                                                 (False, dict(act_order=True))])
+@pytest.mark.parametrize("layer_sharded,extra", [(False, None), (True, None), (False, dict(act_order=True))])
 def test_full_gptq_engine_gloo_world2_matches_single_process(monkeypatch, layer_sharded, extra):
     from tests.host_twins import install_gptq_twins
     from tests.test_api_gpu import tiny_llama
