@@ -8,7 +8,7 @@ from typing import Dict, Tuple
 
 import torch
 
-from ..utils import Mode, get_quantizer, logger, postprocess_model, register_algo
+from ..utils import Mode, dump_model_op_stats, get_quantizer, logger, postprocess_model, register_algo
 from .config import AWQ, GPTQ, RTN, SMOOTH_QUANT, AWQConfig, GPTQConfig, RTNConfig, SmoothQuantConfig
 
 
@@ -50,6 +50,7 @@ def rtn_entry(model: torch.nn.Module, configs_mapping: Dict[Tuple[str, str], RTN
     model.qconfig = configs_mapping
     _bind_save(model)
     postprocess_model(model, mode, quantizer)
+    dump_model_op_stats(mode, configs_mapping)
     return model
 
 
@@ -84,6 +85,7 @@ def gptq_entry(model: torch.nn.Module, configs_mapping: Dict[Tuple[str, str], GP
     model.qconfig = configs_mapping
     _bind_save(model)
     postprocess_model(model, mode, quantizer)
+    dump_model_op_stats(mode, configs_mapping)
     return model
 
 
@@ -129,6 +131,7 @@ def awq_quantize_entry(model: torch.nn.Module, configs_mapping: Dict[Tuple[str, 
     model.qconfig = configs_mapping
     _bind_save(model)
     postprocess_model(model, mode, quantizer)
+    dump_model_op_stats(mode, configs_mapping)
     return model
 
 

@@ -127,3 +127,30 @@ def move_to_device(obj, device):
     if isinstance(obj, dict):
         return {k: move_to_device(v, device) for k, v in obj.items()}
     return obj
+
+
+def dump_model_op_stats(mode, configs_mapping):
+    """torch/utils/utility.py:204-254: the "Mixed Precision Statistics" table logged after convert -- per operator type how
+    many operators ended in which weight format (A32W<bits>G<group_size>) and how many stayed FP32."""
+    if getattr(mode, "value", mode) == Mode.PREPARE.value:
+        return
+    rows, formats = {}, set()
+    for (_name, op_type), cfg in configs_mapping.items():
+        fmt = "FP32" if getattr(cfg, "dtype", "fp32") == "fp32" else "A32W{}G{}".format(getattr(cfg, "bits", "?"),
+                                                                                     getattr(cfg, "group_size", "?"))
+        formats.add(fmt)
+        rows.setdefault(op_type, {})
+        rows[op_type][fmt] = rows[op_type].get(fmt, 0) + 1
+    formats.add("FP32")
+    cols = sorted(formats)
+    header = ["Op Type", "Total"] + cols
+    table = [header] + [[t, sum(c.values())] + [c.get(f, 0) for f in cols] for t, c in rows.items()]
+    widths = [max(len(str(r[i])) for r in table) for i in range(len(header))]
+    line = "+" + "+".join("-" * (w + 2) for w in widths) + "+"
+    logger.info("|" + "Mixed Precision Statistics".center(len(line) - 2, "*") + "|")
+    logger.info(line)
+    for i, r in enumerate(table):
+        logger.info("|" + "|".join(" " + str(v).center(w) + " " for v, w in zip(r, widths)) + "|")
+        if i == 0:
+            logger.info(line)
+    logger.info(line)
