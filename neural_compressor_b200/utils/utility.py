@@ -154,3 +154,93 @@ def dump_model_op_stats(mode, configs_mapping):
         if i == 0:
             logger.info(line)
     logger.info(line)
+
+
+# ------------------------------------------------------------------------------------------------
+# small calibration helpers of weight_only/utility.py (model_forward :546, forward_wrapper :566, move_input_to_device
+# :587, get_example_input :1010, CapturedDataloader :1185, convert_dtype_str2torch :1218)
+# ------------------------------------------------------------------------------------------------
+def move_input_to_device(input, device=torch.device("cpu")):
+    """Tensors inside (nested) dicts / lists / tuples go to `device`; anything else is handed back untouched."""
+    from collections import UserDict
+
+    if isinstance(input, (dict, UserDict)):
+        return {k: move_input_to_device(v, device) for k, v in input.items()}
+    if isinstance(input, (list, tuple)):
+        moved = [move_input_to_device(v, device) for v in input]
+        return tuple(moved) if isinstance(input, tuple) else moved
+    return input.to(device) if isinstance(input, torch.Tensor) else input
+
+
+def forward_wrapper(model, input, device=torch.device("cpu")):
+    """One forward with whatever a dataloader yields: dict -> keywords, list / tuple -> positionals (or, when the model
+    does not take them that way, the sequence itself), anything else -> the single argument."""
+    from collections import UserDict
+
+    try:
+        model = model.to(device)
+        input = move_input_to_device(input, device)
+    except Exception as e:
+        logger.warning(e)
+        logger.warning("Please check the input device if the error raised.")
+    if isinstance(input, (dict, UserDict)):
+        return model(**input)
+    if isinstance(input, (list, tuple)):
+        try:
+            return model(*input)
+        except Exception:
+            return model(input)
+    return model(input)
+
+
+def _batches(dataloader, limit):
+    """(input, label) pairs when the loader yields pairs, the raw batches otherwise -- decided like the reference does, by
+    whether unpacking a batch into two works."""
+    def first(n_items, pick):
+        for i, batch in enumerate(dataloader):
+            if limit != -1 and i >= n_items:
+                break
+            yield pick(batch)
+
+    try:
+        return [inp for inp in first(limit, lambda b: (lambda inp, _label: inp)(*b))]
+    except Exception:
+        return list(first(limit, lambda b: b))
+
+
+def model_forward(model, dataloader, iters, device):
+    """Run `iters` batches (-1: all) of `dataloader` through `model`; labels, when present, are dropped."""
+    for inp in _batches(dataloader, iters):
+        forward_wrapper(model, inp, device)
+
+
+def get_example_input(dataloader, i=1):
+    """The i-th input of the loader (without its label), or the last one when the loader is shorter."""
+    inputs = _batches(dataloader, i + 1)
+    return inputs[min(i, len(inputs) - 1)] if inputs else None
+
+
+class CapturedDataloader:
+    """Replays the (args, kwargs) a model was called with during `run_fn` (weight_only/utility.py:1185-1203)."""
+
+    def __init__(self, args_list, kwargs_list):
+        self.args_list, self.kwargs_list = args_list, kwargs_list
+
+    def __iter__(self):
+        for args, kwargs in zip(self.args_list, self.kwargs_list):
+            if not args:
+                yield kwargs
+            elif not kwargs:
+                yield args[0] if len(args) == 1 else args
+            else:
+                yield args, kwargs
+
+
+def convert_dtype_str2torch(str_dtype):
+    """"fp16" / "float16" / "bf16" / "bfloat16" / "fp32" / "float32" / "auto" / "int8" -> torch dtype."""
+    if isinstance(str_dtype, torch.dtype) or str_dtype is None:
+        return str_dtype
+    table = {"int8": torch.int8, "fp32": torch.float, "float32": torch.float, "auto": torch.float, "fp16": torch.float16,
+             "float16": torch.float16, "bf16": torch.bfloat16, "bfloat16": torch.bfloat16}
+    assert str_dtype in table, "Unsupported str dtype {} to torch dtype".format(str_dtype)
+    return table[str_dtype]
