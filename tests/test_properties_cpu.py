@@ -56,3 +56,76 @@ def test_awq_repack_inverts_the_autoawq_layout(k8, n8, groups, seed):
     aw, az = _optimum_to_autoawq(qweight, qzeros)
     rw, rz, rs = repack_awq_to_optimum_format(aw, az, scales, 4, gs)
     assert torch.equal(rw, qweight) and torch.equal(rz, qzeros) and rs is scales
+
+
+def _live_utility():
+    import pytest
+
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    import neural_compressor.torch.algorithms.weight_only.utility as U
+
+    return U
+
+
+@settings(max_examples=60, deadline=None)
+@given(bits=st.integers(2, 8), sym=st.booleans(), n=st.integers(1, 6), k=st.integers(4, 70),
+       gs=st.sampled_from([-1, 4, 8, 16, 32]), full_range=st.booleans(), quantile=st.sampled_from([1.0, 0.93, 0.805]),
+       dtype=st.sampled_from([torch.float32, torch.float16, torch.bfloat16]), seed=st.integers(0, 2**16))
+def test_oracle_rtn_equals_live_quant_tensor(bits, sym, n, k, gs, full_range, quantile, dtype, seed):
+    """The oracle's restatement of `quant_tensor` on random shapes (ragged tails included), schemes, clip quantiles and
+    storage dtypes -- beyond the fixed fixtures -- bit for bit against the live reference."""
+    from oracle import woq_oracle as O
+
+    U = _live_utility()
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(n, k, generator=g) * 0.05).to(dtype)
+    scheme = "sym" if sym else "asym"
+    q, s, z = U.quant_tensor(w.clone(), bits=bits, group_size=gs, scheme=scheme, quantile=quantile, return_int=True,
+                             full_range=full_range)
+    oq, os_, oz = O.rtn_quantize(w, bits, gs, scheme, quantile, full_range)
+    assert torch.equal(oq.float(), q.float()) and torch.equal(os_.float(), s.float())
+    assert (z is None) == (oz is None) and (z is None or torch.equal(oz.float(), z.float()))
+    fq = U.quant_tensor(w.clone(), bits=bits, group_size=gs, scheme=scheme, quantile=quantile, full_range=full_range)
+    assert torch.equal(O.rtn_fake_quant(w, bits, gs, scheme, quantile, full_range).float(), fq.float())
+
+
+_HOST = {}
+
+
+def _host_f4():
+    """The g++ build of the product's f4_math.cuh (tests/host/f4_host.cpp), built once per session."""
+    if "lib" not in _HOST:
+        import ctypes
+        import os
+        import subprocess
+        import tempfile
+
+        here = os.path.dirname(os.path.abspath(__file__))
+        so = os.path.join(tempfile.mkdtemp(prefix="f4host"), "f4_host.so")
+        subprocess.run(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(here, "host", "f4_host.cpp")],
+                       check=True)
+        _HOST["lib"] = ctypes.CDLL(so)
+    return _HOST["lib"]
+
+
+@settings(max_examples=40, deadline=None)
+@given(name=st.sampled_from(["nf4", "fp4", "fp4_e2m1_bnb", "fp4_e2m1"]), n=st.integers(1, 5), k=st.integers(2, 70),
+       gs=st.sampled_from([-1, 8, 16, 32]), quantile=st.sampled_from([1.0, 0.9, 0.805]),
+       dtype=st.sampled_from([torch.float32, torch.float16, torch.bfloat16]), seed=st.integers(0, 2**16))
+def test_f4_kernel_math_equals_live_quantize_4bit(name, n, k, gs, quantile, dtype, seed):
+    """csrc/f4_math.cuh (host build) against the live reference's `quantize_4bit` on random shapes, group sizes (ragged
+    tails), clip quantiles and storage dtypes: integer codes, scales and fake-quantised values, bit for bit."""
+    from tests.test_rtn_dtypes_cpu import host_quantize
+
+    U = _live_utility()
+    g = torch.Generator().manual_seed(seed)
+    w = (torch.randn(n, k, generator=g) * 0.05).to(dtype)
+    q, s, _ = U.quant_tensor(w.clone(), dtype=name, group_size=gs, quantile=quantile, return_int=True)
+    fq = U.quant_tensor(w.clone(), dtype=name, group_size=gs, quantile=quantile)
+    codes, scale, fake = host_quantize(_host_f4(), w, name, gs, quantile)
+    assert torch.equal(codes.float(), q.float()) and torch.equal(scale, s.float())
+    assert torch.equal(torch.nan_to_num(fake, nan=7.0), torch.nan_to_num(fq.float(), nan=7.0))
