@@ -129,3 +129,47 @@ def test_f4_kernel_math_equals_live_quantize_4bit(name, n, k, gs, quantile, dtyp
     codes, scale, fake = host_quantize(_host_f4(), w, name, gs, quantile)
     assert torch.equal(codes.float(), q.float()) and torch.equal(scale, s.float())
     assert torch.equal(torch.nan_to_num(fake, nan=7.0), torch.nan_to_num(fq.float(), nan=7.0))
+
+
+@settings(max_examples=30, deadline=None)
+@given(bits=st.sampled_from([2, 3, 4, 8]), sym=st.booleans(), n=st.integers(2, 12), groups=st.integers(1, 4),
+       gs=st.sampled_from([8, 16, 32]), blocksize=st.sampled_from([8, 16, 32, 2048]), act_order=st.booleans(),
+       mse=st.booleans(), seed=st.integers(0, 2**16))
+def test_oracle_gptq_equals_live_fasterquant(bits, sym, n, groups, gs, blocksize, act_order, mse, seed):
+    """The oracle's Hessian accumulation + `fasterquant` restatement against the live reference's GPTQ class on random
+    layer shapes, block sizes (smaller than, equal to and larger than the group), act_order, the mse grid, a dead input
+    channel and an outlier one: fake-quantised weights, scales and zeros bit for bit."""
+    import pytest
+
+    from oracle import woq_oracle as O
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    from neural_compressor.torch.algorithms.weight_only.gptq import GPTQ
+
+    if blocksize < gs:            # the engine's contract: a block is a multiple of the group (or the whole layer)
+        blocksize = gs
+    C = gs * groups
+    g = torch.Generator().manual_seed(seed)
+    lin = torch.nn.Linear(C, n, bias=False)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(n, C, generator=g) * 0.05)
+    X = [torch.randn(1, 3 * C, C, generator=g) for _ in range(3)]
+    for x in X:
+        x[..., 1] *= 5.0
+        if C > 8:
+            x[..., 5] = 0.0
+    gp = GPTQ(lin, lin.weight.data.clone(), "cpu")
+    gp.quantizer.configure(dict(dtype="int", bits=bits, sym=sym, group_size=gs, mse=mse, perchannel=True,
+                                use_double_quant=False, double_quant_sym=False))
+    oracle = O.GPTQLayerOracle(n, C, bits=bits, sym=sym, mse=mse)
+    for x in X:
+        gp.add_batch(x, None)
+        oracle.add_batch(x)
+    assert torch.equal(oracle.H, gp.H)
+    scale, _, zero, Q = gp.fasterquant(lin.weight.data.clone(), blocksize=blocksize, percdamp=0.01, groupsize=gs,
+                                       act_order=act_order)
+    r = oracle.fasterquant(lin.weight.data.clone(), blocksize=blocksize, percdamp=0.01, groupsize=gs, act_order=act_order)
+    assert torch.equal(r["Q"], Q.float()) and torch.equal(r["scale"], scale) and torch.equal(r["zero"], zero)
