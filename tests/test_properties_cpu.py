@@ -173,3 +173,38 @@ def test_oracle_gptq_equals_live_fasterquant(bits, sym, n, groups, gs, blocksize
                                        act_order=act_order)
     r = oracle.fasterquant(lin.weight.data.clone(), blocksize=blocksize, percdamp=0.01, groupsize=gs, act_order=act_order)
     assert torch.equal(r["Q"], Q.float()) and torch.equal(r["scale"], scale) and torch.equal(r["zero"], zero)
+
+
+@settings(max_examples=40, deadline=None)
+@given(bits=st.sampled_from([2, 3, 4, 8]), sym=st.booleans(), n=st.integers(1, 20), k=st.integers(8, 80),
+       gs=st.sampled_from([-1, 8, 16, 32]), seed=st.integers(0, 2**16))
+def test_oracle_pack_recover_forward_equal_live_module(bits, sym, n, k, gs, seed):
+    """The oracle's optimum-format pack / unpack / recover / forward against the live `INCWeightOnlyLinear` on random
+    shapes (K not a multiple of n_pack or of the group, N not a multiple of n_pack), widths and schemes."""
+    import pytest
+
+    from oracle import woq_oracle as O
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    from neural_compressor.torch.algorithms.weight_only.modules import INCWeightOnlyLinear
+    from neural_compressor.torch.algorithms.weight_only.utility import quant_tensor
+
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(n, k, generator=g) * 0.05
+    bias = torch.randn(n, generator=g) * 0.01
+    scheme = "sym" if sym else "asym"
+    q, s, z = quant_tensor(w.clone(), bits=bits, group_size=gs, scheme=scheme, return_int=True)
+    group = k if gs == -1 or k < gs else gs
+    m = INCWeightOnlyLinear(k, n, dtype="int", bits=bits, group_size=group, zp=z is not None, bias=True, device="cpu")
+    m.pack(q.clone(), s.clone(), None if z is None else z.clone(), bias)
+    qweight, qzeros, scales = O.pack_optimum(q, s, z, bits, group)
+    assert torch.equal(qweight, m.qweight) and torch.equal(qzeros, m.qzeros) and torch.equal(scales, m.scales)
+    rec = m.recover()
+    assert torch.equal(O.recover_fp16(qweight, qzeros, scales, bits, group, k, n).float(), rec.float())
+    x = torch.randn(3, k, generator=g)
+    want = m(x)
+    got = O.woq_linear_forward(x, qweight, qzeros, scales, m.bias, bits, group, k, n)
+    assert torch.allclose(got.float(), want.float(), rtol=1e-5, atol=1e-6)
