@@ -1,0 +1,50 @@
+"""save -> load round trips of models produced by the engines' host flows (kernels = oracle twins): GPTQ with act_order
+(g_idx) in both on-disk formats, AWQ with its MulLinear wrappers in the default format.  Loading runs on the host."""
+import pytest
+import torch
+
+from tests.test_awq_absorb_cpu import host_ops as awq_host_ops  # noqa: F401  (fixture)
+
+
+@pytest.fixture()
+def gptq_host_ops(monkeypatch):
+    from tests.host_twins import install_gptq_twins
+    install_gptq_twins(running_mean=True, setter=monkeypatch.setattr)
+    monkeypatch.setenv("B200WOQ_CALIB_BATCH", "1")
+
+def test_gptq_act_order_roundtrip(gptq_host_ops, golden_e2e, tmp_path):
+    import neural_compressor_b200.quantization as api
+    from tests.test_api_gpu import tiny_llama
+    m = api.prepare(tiny_llama(golden_e2e["init_state"]), api.GPTQConfig(bits=4, group_size=32, act_order=True))
+    for x in golden_e2e["ids"]:
+        m(x)
+    m = api.convert(m)
+    for fmt in ("default", "huggingface"):
+        d = tmp_path / fmt
+        m.save(str(d), format=fmt)
+        if fmt == "default":
+            loaded = api.load(str(d), original_model=tiny_llama(golden_e2e["init_state"]), device="cpu")
+        else:
+            loaded = api.load(str(d), format="huggingface", device="cpu")
+        a, b = m.state_dict(), loaded.state_dict()
+        keys = [k for k in a if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales", "g_idx")]
+        assert len(keys) == 56
+        for k in keys:
+            assert torch.equal(a[k], b[k]), (fmt, k)
+
+def test_awq_roundtrip(awq_host_ops, golden_e2e, tmp_path):  # noqa: F811
+    import neural_compressor_b200.quantization as api
+    from tests.test_api_gpu import tiny_llama
+    ids = golden_e2e["ids"]
+    def run_fn(model):
+        for x in ids:
+            model(x)
+    m = api.quantize(tiny_llama(golden_e2e["init_state"]), api.AWQConfig(bits=4, group_size=32, use_sym=False), run_fn=run_fn, example_inputs=ids[0])
+    m.save(str(tmp_path))
+    loaded = api.load(str(tmp_path), original_model=tiny_llama(golden_e2e["init_state"]), device="cpu")
+    a, b = m.state_dict(), loaded.state_dict()
+    keys = [k for k in a if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales", "input_scale")]
+    assert len(keys) == 56
+    for k in keys:
+        assert torch.equal(a[k], b[k]), k
+    assert type(loaded.model.layers[0].self_attn.q_proj).__name__ == "MulLinear"
