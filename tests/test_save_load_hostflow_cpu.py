@@ -48,3 +48,37 @@ def test_awq_roundtrip(awq_host_ops, golden_e2e, tmp_path):  # noqa: F811
     for k in keys:
         assert torch.equal(a[k], b[k]), k
     assert type(loaded.model.layers[0].self_attn.q_proj).__name__ == "MulLinear"
+
+
+def test_the_live_reference_loads_our_default_format_checkpoint(golden_e2e, tmp_path, monkeypatch):
+    """Interop the other way round: a checkpoint written by `model.save()` here (quantized_weight.pt + qconfig.json) is
+    read by the UNMODIFIED reference's `load(..., original_model=...)`, which rebuilds its own INCWeightOnlyLinear modules
+    from it; the logits equal those of the model the reference quantised itself (tests/golden/e2e_tiny_llama.pt)."""
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    import neural_compressor.torch.quantization as ref
+
+    import neural_compressor_b200.quantization as api
+    from neural_compressor_b200 import ops
+    from neural_compressor_b200.algorithms import rtn
+    from oracle import woq_oracle as O
+    from tests.test_api_gpu import tiny_llama
+
+    def rtn_quant_pack(W, bits=4, group_size=-1, sym=False, full_range=False, quantile=1.0, return_codes=False):
+        q, s, z = O.rtn_quantize(W, bits, group_size, "sym" if sym else "asym", quantile, full_range)
+        qweight, qzeros, scales16 = O.pack_optimum(q, s, z, bits, group_size)
+        return dict(qweight=qweight, qzeros=qzeros, scales=scales16, scale_f32=s.float(), zp_f32=None if z is None else z.float())
+
+    monkeypatch.setattr(ops, "rtn_quant_pack", rtn_quant_pack)
+    monkeypatch.setattr(rtn, "current_device", lambda: torch.device("cpu"))
+    m = api.convert(api.prepare(tiny_llama(golden_e2e["init_state"]),
+                                api.RTNConfig(bits=4, group_size=32, use_sym=False, use_layer_wise=False)))
+    m.save(str(tmp_path))
+    loaded = ref.load(str(tmp_path), original_model=tiny_llama(golden_e2e["init_state"]))
+    assert type(loaded.model.layers[0].self_attn.q_proj).__name__ == "INCWeightOnlyLinear"
+    with torch.no_grad():
+        out = loaded(golden_e2e["probe"]).logits
+    assert torch.equal(out, golden_e2e["rtn_asym"]["logits"])
