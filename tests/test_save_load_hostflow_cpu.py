@@ -82,3 +82,26 @@ def test_the_live_reference_loads_our_default_format_checkpoint(golden_e2e, tmp_
     with torch.no_grad():
         out = loaded(golden_e2e["probe"]).logits
     assert torch.equal(out, golden_e2e["rtn_asym"]["logits"])
+
+
+def test_we_load_a_checkpoint_saved_by_the_live_reference(golden_e2e, tmp_path):
+    """... and the other direction: `quantized_weight.pt` + `qconfig.json` written by the reference's own `model.save()`
+    are read by `load()` here into B200WeightOnlyLinear modules holding the identical tensors."""
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("reference tree not present")
+    load_reference()
+    import neural_compressor.torch.quantization as ref
+
+    import neural_compressor_b200.quantization as api
+    from tests.test_api_gpu import tiny_llama
+
+    m = ref.convert(ref.prepare(tiny_llama(golden_e2e["init_state"]),
+                                ref.RTNConfig(bits=4, group_size=32, use_sym=False, use_layer_wise=False)))
+    m.save(str(tmp_path))
+    loaded = api.load(str(tmp_path), original_model=tiny_llama(golden_e2e["init_state"]), device="cpu")
+    assert type(loaded.model.layers[0].self_attn.q_proj).__name__ == "B200WeightOnlyLinear"
+    a, b = m.state_dict(), loaded.state_dict()
+    keys = [k for k in a if k.rsplit(".", 1)[-1] in ("qweight", "qzeros", "scales")]
+    assert len(keys) == 42 and all(torch.equal(a[k], b[k]) for k in keys)
